@@ -1,0 +1,145 @@
+/* oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU oracle for the DoonEngine per-voxel lighting + ray-cast draw path.
+ * Nothing in the product (doonengine_b200/, include/) may include, link or
+ * execute anything under oracle/.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs use it, as the checker.
+ *
+ * The oracle works on buffers in the REFERENCE's GPU layout (the SSBOs the
+ * GLSL shaders bind), so that the bytes produced by the reference's own host
+ * code (oracle/_ref, "Oracle A") can be fed to it unchanged:
+ *
+ *   binding 0  map[]     OrbHandle   12 B   assets/shaders/voxelShared.comp:49-54,74-77
+ *   binding 1  chunks[]  OrbChunk    96 B   voxelShared.comp:39-46,80-83 ; voxel.c:25-34
+ *   binding 2  materials OrbMaterial 32 B   voxelShared.comp:57-69,86-89 ; voxel.h:82-94
+ *   binding 3  requests  uint32             voxelLighting.comp:7-10
+ *   binding 4  voxels[]  OrbVoxel    16 B   voxelShared.comp:30-36,92-95 ; voxel.c:16-22
+ *
+ * Parity status: the reference ships no tests, golden vectors or KATs for the
+ * GLSL arithmetic and no GLSL implementation can run
+ * in the build container or on the GPU box.  The HOST half of the path is
+ * pinned by Oracle A (the reference's own voxel.c compiled in place behind a
+ * fake-GL shim, oracle/fake_gl.c).  The SHADER half (this restatement) is
+ * "parity unpinned by the reference": its fidelity rests on the line-by-line
+ * citations in shader_cpu.c and on the determinism rules N1-N10 below.
+ *
+ * Determinism rules added where the reference is racy / implementation
+ * defined:
+ *   N1  rays read voxel records as they were BEFORE the lighting dispatch.
+ *   N2  every work-group sees the pre-dispatch numIndirectSamples; it is
+ *       incremented once per chunk afterwards.
+ *   N3  visible bit: lighting first clears it for every chunk that had at
+ *       least one live invocation, then ORs in specular propagations whose
+ *       source chunk was visible pre-dispatch.  Draw ORs.
+ *   N4  lastUsed = 0 writes are performed (benign).
+ *   N5  sin() = glibc sinf on the host.
+ *   N6  normalize(v) = v * (1/sqrt(dot(v,v))), IEEE div and sqrt; dot is
+ *       x*x + y*y + z*z left to right; no FMA contraction anywhere;
+ *       min/max = IEEE minNum/maxNum (fminf/fmaxf); round = nearest-even;
+ *       reflect = I - 2*dot(N,I)*N; refract per the GLSL spec formula;
+ *       mix(a,b,t) = a*(1-t) + b*t; pow = powf; sign(NaN) = 0.
+ *       vec3(mask)*x in iterate_DDA is evaluated as a select (mask ? x : 0),
+ *       which differs from the literal product only for infinite deltaDist
+ *       (a ray direction component that is exactly 0), where GLSL is undefined.
+ *   N7  alpha of pixels whose ray misses the map box is written as -1.
+ *   N8  the `voxel` out-parameter keeps its previous value when not written.
+ *   N9  `time` is supplied by the harness.
+ *   N11 (added) every DDA loop carries an iteration guard (ORB_MAX_*_STEPS);
+ *       the reference would spin forever on NaN directions.  A ray that
+ *       trips the guard is a miss.
+ */
+#ifndef DN_ORACLE_H
+#define DN_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrbHandle   { uint32_t flags, lastUsed, voxelIndex; } OrbHandle;
+typedef struct OrbChunk    { int32_t pos[3]; uint32_t numIndirectSamples; uint32_t partialCounts[3]; uint32_t bitMask[16]; uint32_t pad; } OrbChunk;
+typedef struct OrbVoxel    { uint32_t normal, albedo, specLight, diffuseLight; } OrbVoxel;
+typedef struct OrbMaterial { float pad[2]; uint32_t emissive; float opacity, refractIndex, specular; uint32_t reflectType, shininess; } OrbMaterial;
+
+/* every uniform the two programs read (voxel.c:856-876 and voxel.c:922-947) */
+typedef struct OrbUniforms
+{
+	uint32_t mapSize[3];
+	uint32_t useCubemap;              /* must be 0: cubemap sampling is out of scope */
+	float    skyGradientBot[3];
+	float    skyGradientTop[3];
+	float    sunStrength[3];
+	float    ambientStrength[3];
+	/* draw only */
+	uint32_t viewMode;
+	uint32_t composeRasterized;       /* must be 0 */
+	float    invViewMat[16];          /* column-major, m[col][row] flattened */
+	float    invCenteredViewMat[16];
+	float    invProjectionMat[16];
+	/* lighting only */
+	float    time;
+	uint32_t numDiffuseSamples;
+	uint32_t maxDiffuseSamples;
+	uint32_t diffuseBounceLimit;
+	uint32_t specularBounceLimit;
+	float    sunDir[3];               /* already normalised on the host, voxel.c:942 */
+	float    shadowSoftness;
+	float    camPos[3];
+} OrbUniforms;
+
+typedef struct OrbBuffers
+{
+	OrbHandle*         map;
+	OrbChunk*          chunks;
+	OrbVoxel*          voxels;
+	const OrbMaterial* materials;     /* 256 entries */
+} OrbBuffers;
+
+/* traversal counters used for the ALGORITHMIC byte count */
+typedef struct OrbCounters
+{
+	uint64_t rays;        /* step_map calls */
+	uint64_t tiles;       /* T: map tiles visited (get_map_tile calls) */
+	uint64_t chunks;      /* C: loaded chunks entered (step_chunk calls) */
+	uint64_t voxelSteps;  /* voxel-level DDA iterations */
+	uint64_t records;     /* H: voxel records fetched inside step_chunk */
+	uint64_t voxelsLit;   /* V: live lighting invocations */
+	uint64_t pixels;      /* P: pixels written */
+} OrbCounters;
+
+/* per-pixel first-hit record written by orb_draw */
+typedef struct OrbHit
+{
+	int32_t  status;      /* 0 = ray misses the map box, 1 = enters the box but hits nothing, 2 = hit */
+	uint32_t mapIndex;    /* tile of the hit voxel (flattened) */
+	uint32_t localIndex;  /* x + 8*(y + 8*z) inside the chunk */
+	uint32_t recordIndex; /* index into voxels[] */
+} OrbHit;
+
+#define ORB_EPSILON 0.0001f
+#define ORB_MAX_CHUNK_STEPS 4096   /* N11 */
+
+/* voxelDraw.comp main() over (w/16)x(h/16) work-groups of 16x16.
+ * image: h*w*4 floats, row-major, row 0 = screen y -1. Pixels outside the
+ * dispatched area are left untouched.  hits may be NULL. */
+void orb_draw(const OrbBuffers* buf, const OrbUniforms* u, int w, int h, float* image, OrbHit* hits, OrbCounters* counters);
+
+/* voxelLighting.comp main() over numRequests work-groups of 32, with the
+ * snapshot semantics N1-N3.  Updates voxels[], chunks[].numIndirectSamples
+ * and map[].flags in place. */
+void orb_light(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t numRequests, size_t numVoxelRecords, OrbCounters* counters);
+
+/* helpers exposed for unit tests */
+uint32_t orb_get_voxel_index(const OrbBuffers* buf, uint32_t mapIndex, int x, int y, int z);
+void     orb_get_voxel_position(const OrbBuffers* buf, uint32_t chunk, uint32_t voxNum, int out[3]);
+float    orb_rand(float seed);
+void     orb_rand_unit_sphere(float seed, float out[3]);
+int      orb_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
