@@ -1,0 +1,1140 @@
+/* engine.cpp -- the device half of the DN_* API: CUDA context, HBM allocations, chunk packing and upload,
+ * DN_sync_gpu / DN_draw / DN_update_lighting, and the additive DN_b200_* entry points.
+ *
+ * Reference functions re-hosted here (all in /root/reference/src/DoonEngine/voxel.c):
+ *   DN_init/DN_quit 119-163, DN_sync_gpu 719-786 (+ _DN_request_chunk_lighting 1463-1489 -> compact.cu,
+ *   _DN_stream_to_gpu 1491-1536, _DN_chunk_to_gpu 1391-1461, _DN_stream_chunk/_DN_stream_voxels 1548-1640 -> upload.cu),
+ *   DN_draw 812-881, DN_update_lighting 883-952, DN_set_max_voxels_gpu 1031-1082.
+ * There is NO CPU fallback: without a CUDA device DN_init fails and nothing else works.
+ */
+#include "engine.h"
+#include "hostmath.h"
+
+#include <algorithm>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <thread>
+
+namespace dnb
+{
+
+static Context g_ctx;
+Context& ctx() { return g_ctx; }
+static int g_requestedDevice = -1;
+
+bool cuda_ok(cudaError_t e, const char* what)
+{
+	if(e == cudaSuccess)
+		return true;
+	report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+	return false;
+}
+
+template <typename T> void device_free(DeviceArray<T>& a)
+{
+	if(a.ptr)
+		cudaFree(a.ptr);
+	a.ptr = nullptr;
+	a.cap = 0;
+}
+
+/* grows `a` to at least `count` elements on the compute stream; `keep` copies the old contents, `zeroNew` clears the rest */
+template <typename T> bool device_reserve(DeviceArray<T>& a, size_t count, bool keep, bool zeroNew, const char* what)
+{
+	if(count <= a.cap)
+		return true;
+	cudaStream_t s = ctx().stream();
+	T* fresh = nullptr;
+	if(!cuda_ok(cudaMalloc((void**)&fresh, count * sizeof(T)), what))
+		return false;
+	if(a.ptr)
+	{
+		/* the old block may still be written or read by queued work of either stream */
+		cudaStreamSynchronize(ctx().uploadStream);
+		cudaStreamSynchronize(s);
+	}
+	size_t kept = 0;
+	if(a.ptr && keep)
+	{
+		kept = a.cap;
+		cuda_ok(cudaMemcpyAsync(fresh, a.ptr, kept * sizeof(T), cudaMemcpyDeviceToDevice, s), what);
+	}
+	if(zeroNew)
+		cuda_ok(cudaMemsetAsync(fresh + kept, 0, (count - kept) * sizeof(T), s), what);
+	if(a.ptr)
+	{
+		cudaStreamSynchronize(s);
+		cudaFree(a.ptr);
+	}
+	a.ptr = fresh;
+	a.cap = count;
+	return true;
+}
+
+static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+bool device_create(VolumeImpl* v)
+{
+	const DNvolume* vol = &v->pub;
+	const size_t tiles = num_tiles(vol);
+	const size_t words = (tiles + 31) / 32;
+	for(int a = 0; a < 3; a++)
+		v->blocks[a] = div_up((&vol->mapSize.x)[a], 4);
+	const size_t numBlocks = (size_t)v->blocks[0] * v->blocks[1] * v->blocks[2];
+
+	bool ok = true;
+	ok = ok && device_reserve(v->tileSlot, tiles ? tiles : 1, false, true, "tile table");
+	ok = ok && device_reserve(v->occ64, numBlocks ? numBlocks : 1, false, true, "occupancy bitmap");
+	ok = ok && device_reserve(v->visible, words ? words : 1, false, true, "visible bitmap");
+	ok = ok && device_reserve(v->propagate, words ? words : 1, false, true, "propagate bitmap");
+	ok = ok && device_reserve(v->forced, words ? words : 1, false, true, "forced bitmap");
+	ok = ok && device_reserve(v->materials, DN_MAX_MATERIALS, false, true, "materials");
+	ok = ok && device_reserve(v->slots, std::max<size_t>(vol->chunkCap, 64), false, true, "chunk slots");
+	ok = ok && device_reserve(v->records, std::max<size_t>(vol->voxelCap, 4096), false, true, "voxel records");
+	ok = ok && device_reserve(v->requests, 1024, false, false, "lighting requests");
+	const uint32_t cb = dnb_compact_num_blocks((uint32_t)tiles);
+	ok = ok && device_reserve(v->blockCounts, cb ? cb : 1, false, true, "compaction counts");
+	ok = ok && device_reserve(v->blockOffsets, cb ? cb : 1, false, true, "compaction offsets");
+	ok = ok && device_reserve(v->scalars, 16, false, true, "scalars");
+	if(ok && !v->pinnedScalars)
+		ok = cuda_ok(cudaMallocHost((void**)&v->pinnedScalars, 16 * sizeof(uint32_t)), "pinned scalars");
+	if(!ok)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "failed to allocate device memory for a %ux%ux%u map", vol->mapSize.x, vol->mapSize.y, vol->mapSize.z);
+		return false;
+	}
+	v->pub.voxelCap = v->records.cap;
+	v->pub.glMapBufferID = 1;
+	v->pub.glChunkBufferID = 2;
+	v->pub.glVoxelBufferID = 3;
+	return true;
+}
+
+void device_destroy(VolumeImpl* v)
+{
+	if(ctx().ready)
+	{
+		cudaStreamSynchronize(ctx().stream());
+		cudaStreamSynchronize(ctx().uploadStream);
+	}
+	device_free(v->tileSlot); device_free(v->occ64); device_free(v->visible); device_free(v->propagate); device_free(v->forced);
+	device_free(v->slots); device_free(v->records); device_free(v->materials); device_free(v->requests); device_free(v->staging);
+	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->blob);
+	if(v->pinnedBlob) cudaFreeHost(v->pinnedBlob);
+	if(v->pinnedScalars) cudaFreeHost(v->pinnedScalars);
+	if(v->counters) cudaFree(v->counters);
+	v->pinnedBlob = nullptr;
+	v->pinnedBlobCap = 0;
+	v->pinnedScalars = nullptr;
+	v->counters = nullptr;
+}
+
+void fill_scene(VolumeImpl* v, DnbScene* s)
+{
+	const DNvolume* vol = &v->pub;
+	memset(s, 0, sizeof(*s));
+	s->mapSize[0] = vol->mapSize.x; s->mapSize[1] = vol->mapSize.y; s->mapSize[2] = vol->mapSize.z;
+	s->blocks[0] = v->blocks[0]; s->blocks[1] = v->blocks[1]; s->blocks[2] = v->blocks[2];
+	s->numTiles = (uint32_t)num_tiles(vol);
+	s->maxMapSteps = 4u * (vol->mapSize.x + vol->mapSize.y + vol->mapSize.z) + 256u;
+	s->occ64 = v->occ64.ptr;
+	s->tileSlot = v->tileSlot.ptr;
+	s->slots = v->slots.ptr;
+	s->records = v->records.ptr;
+	s->materials = v->materials.ptr;
+	s->visible = v->visible.ptr;
+	s->propagate = v->propagate.ptr;
+	s->counters = v->counters;
+	memcpy(s->skyBot, &vol->skyGradientBot, 12);
+	memcpy(s->skyTop, &vol->skyGradientTop, 12);
+	memcpy(s->sunStrength, &vol->sunStrength, 12);
+	memcpy(s->ambient, &vol->ambientLightStrength, 12);
+}
+
+/* ---- timing helpers: device time of a kernel group, only when DN_b200_enable_timing(true) ---- */
+struct ScopedTimer
+{
+	float* out;
+	cudaStream_t s;
+	ScopedTimer(float* dst, cudaStream_t stream) : out(dst), s(stream)
+	{
+		if(ctx().timing)
+			cudaEventRecord(ctx().evT0, s);
+	}
+	~ScopedTimer()
+	{
+		if(ctx().timing)
+		{
+			cudaEventRecord(ctx().evT1, s);
+			cudaEventSynchronize(ctx().evT1);
+			cudaEventElapsedTime(out, ctx().evT0, ctx().evT1);
+		}
+	}
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* chunk packing: voxel.c:1391-1461                                                                   */
+
+static inline bool face_open(const DNvolume* vol, const DNchunk* c, int x, int y, int z)
+{
+	if((unsigned)x >= 8u || (unsigned)y >= 8u || (unsigned)z >= 8u)
+		return true; /* culling is chunk-local: border voxels are always kept */
+	const uint32_t mat = c->voxels[x][y][z].normal >> 24;
+	return mat == DN_MATERIAL_EMPTY || vol->materials[mat].opacity < 1.0f;
+}
+
+/* fills the slot header (everything but voxelBase) and the records in local-index order; returns the record count */
+static uint32_t pack_chunk(const DNvolume* vol, const DNchunk* c, uint32_t mapIndex, DnbSlot* slot, uint4* records)
+{
+	const uint8_t* lut = ctx().albedoLut;
+	memset(slot, 0, sizeof(*slot));
+	slot->mapIndex = mapIndex;
+	slot->pos[0] = c->pos.x; slot->pos[1] = c->pos.y; slot->pos[2] = c->pos.z;
+	slot->numSamples = 0; /* an edit restarts the accumulation (voxel.c:1401) */
+
+	uint32_t n = 0;
+	for(int z = 0; z < 8; z++)
+		for(int y = 0; y < 8; y++)
+		{
+			const uint32_t rowIndex = (uint32_t)(8 * (y + 8 * z));
+			if((rowIndex & 31u) == 0)
+				slot->prefix[rowIndex >> 5] = (uint16_t)n;
+			for(int x = 0; x < 8; x++)
+			{
+				const DNcompressedVoxel vx = c->voxels[x][y][z];
+				if((vx.normal >> 24) == DN_MATERIAL_EMPTY)
+					continue;
+				if(!(face_open(vol, c, x + 1, y, z) || face_open(vol, c, x - 1, y, z) || face_open(vol, c, x, y + 1, z) ||
+				     face_open(vol, c, x, y - 1, z) || face_open(vol, c, x, y, z + 1) || face_open(vol, c, x, y, z - 1)))
+					continue;
+
+				const uint32_t index = rowIndex + (uint32_t)x;
+				slot->mask[index >> 5] |= 1u << (index & 31u);
+				uint4 rec;
+				rec.x = vx.normal;
+				rec.y = ((uint32_t)lut[vx.albedo >> 24] << 24) | ((uint32_t)lut[(vx.albedo >> 16) & 0xFF] << 16) | ((uint32_t)lut[(vx.albedo >> 8) & 0xFF] << 8);
+				rec.z = 0;
+				rec.w = 0;
+				records[n++] = rec;
+			}
+		}
+	slot->numVoxels = n;
+	return n;
+}
+
+/* ---- record-pool allocator: power-of-two nodes of 16..512 records, per-class free lists over a bump pointer ---- */
+static inline int node_class(uint32_t n)
+{
+	int c = 0;
+	uint32_t size = 16;
+	while(size < n) { size <<= 1; c++; }
+	return c;
+}
+
+static void release_slot(VolumeImpl* v, uint32_t slot)
+{
+	const uint8_t cls = v->slotNodeClass[slot];
+	if(cls != 0xFF)
+	{
+		v->freeNodes[cls].push_back(v->slotNodeStart[slot]);
+		v->slotNodeClass[slot] = 0xFF;
+		v->pub.numVoxelNodes--;
+		v->stats.residentRecords -= v->slotNumVoxels[slot];
+		v->slotNumVoxels[slot] = 0;
+	}
+}
+
+static uint32_t acquire_node(VolumeImpl* v, uint32_t slot, uint32_t n)
+{
+	const int cls = node_class(n);
+	uint32_t start;
+	if(!v->freeNodes[cls].empty())
+	{
+		start = v->freeNodes[cls].back();
+		v->freeNodes[cls].pop_back();
+	}
+	else
+	{
+		start = (uint32_t)v->recordTop;
+		v->recordTop += (size_t)16 << cls;
+	}
+	v->slotNodeStart[slot] = start;
+	v->slotNodeClass[slot] = (uint8_t)cls;
+	v->slotNumVoxels[slot] = n;
+	v->stats.residentRecords += n;
+	v->pub.numVoxelNodes++;
+	return start;
+}
+
+static uint32_t acquire_slot(VolumeImpl* v)
+{
+	uint32_t slot;
+	if(!v->freeSlots.empty())
+	{
+		slot = v->freeSlots.back();
+		v->freeSlots.pop_back();
+	}
+	else
+	{
+		slot = v->slotTop++;
+		v->slotNodeStart.push_back(0);
+		v->slotNodeClass.push_back(0xFF);
+		v->slotNumVoxels.push_back(0);
+	}
+	return slot;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* the writing half of DN_sync_gpu: reconcile touched tiles with the device (voxel.c:1491-1536, resident mode) */
+
+struct PendingItem
+{
+	uint32_t tile;
+	uint32_t chunkIndex;
+	bool     remove;
+};
+
+static const size_t UPLOAD_BATCH = 16384; /* chunks per batch: bounds the pinned blob at ~131 MiB */
+
+static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
+{
+	DNvolume* vol = &v->pub;
+	Context& c = ctx();
+
+	/* blob layout: [items][headers][records, 512 per item worst case], identical on host (pinned) and device */
+	const size_t offItems = 0;
+	const size_t offHeaders = (count * sizeof(DnbUploadItem) + 127) & ~(size_t)127;
+	const size_t offRecords = offHeaders + count * sizeof(DnbSlot);
+	const size_t blobBytes = offRecords + count * 512 * sizeof(uint4);
+
+	if(blobBytes > v->pinnedBlobCap)
+	{
+		/* the previous batch may still be in flight from this buffer */
+		cudaStreamSynchronize(c.uploadStream);
+		if(v->pinnedBlob)
+			cudaFreeHost(v->pinnedBlob);
+		v->pinnedBlob = nullptr;
+		v->pinnedBlobCap = 0;
+		if(!cuda_ok(cudaMallocHost((void**)&v->pinnedBlob, blobBytes), "pinned upload blob"))
+			return false;
+		v->pinnedBlobCap = blobBytes;
+	}
+	else
+		cudaStreamSynchronize(c.uploadStream); /* single staging buffer: wait for the previous batch's copy */
+	if(!device_reserve(v->blob, blobBytes, false, false, "device upload blob"))
+		return false;
+
+	DnbUploadItem* hItems = reinterpret_cast<DnbUploadItem*>(v->pinnedBlob + offItems);
+	DnbSlot* hHeaders = reinterpret_cast<DnbSlot*>(v->pinnedBlob + offHeaders);
+	uint4* hRecords = reinterpret_cast<uint4*>(v->pinnedBlob + offRecords);
+
+	/* parallel pack: worker t owns a contiguous range of items and packs their records back to back into its arena */
+	unsigned workers = 1;
+	if(count >= 256)
+	{
+		workers = std::thread::hardware_concurrency();
+		if(workers == 0) workers = 4;
+		workers = std::min<unsigned>(workers, 32);
+		workers = std::min<unsigned>(workers, (unsigned)(count / 64));
+		if(workers == 0) workers = 1;
+	}
+	std::vector<size_t> arenaUsed(workers, 0);
+	auto work = [&](unsigned t)
+	{
+		const size_t begin = count * t / workers, end = count * (t + 1) / workers;
+		size_t cursor = begin * 512;
+		for(size_t i = begin; i < end; i++)
+		{
+			hItems[i].mapIndex = items[i].tile;
+			hItems[i].slotPlus1 = 0;
+			hItems[i].recordOffset = (uint32_t)cursor;
+			hItems[i].pad = 0;
+			if(items[i].remove)
+			{
+				memset(&hHeaders[i], 0, sizeof(DnbSlot));
+				continue;
+			}
+			cursor += pack_chunk(vol, &vol->chunks[items[i].chunkIndex], items[i].tile, &hHeaders[i], hRecords + cursor);
+		}
+		arenaUsed[t] = cursor - begin * 512;
+	};
+	if(workers == 1)
+		work(0);
+	else
+	{
+		std::vector<std::thread> pool;
+		for(unsigned t = 1; t < workers; t++)
+			pool.emplace_back(work, t);
+		work(0);
+		for(auto& th : pool)
+			th.join();
+	}
+
+	/* serial: slots and record nodes */
+	size_t recordBytes = 0;
+	for(size_t i = 0; i < count; i++)
+	{
+		const uint32_t tile = items[i].tile;
+		uint32_t slotPlus1 = v->tileSlotHost[tile];
+		if(items[i].remove)
+		{
+			if(slotPlus1)
+			{
+				release_slot(v, slotPlus1 - 1);
+				v->freeSlots.push_back(slotPlus1 - 1);
+				v->tileSlotHost[tile] = 0;
+				v->stats.chunksRemoved++;
+				v->stats.residentChunks--;
+			}
+			continue;
+		}
+		const uint32_t n = hHeaders[i].numVoxels;
+		if(slotPlus1)
+			release_slot(v, slotPlus1 - 1);
+		else
+		{
+			slotPlus1 = acquire_slot(v) + 1;
+			v->tileSlotHost[tile] = slotPlus1;
+			v->stats.residentChunks++;
+		}
+		hHeaders[i].voxelBase = acquire_node(v, slotPlus1 - 1, n);
+		hItems[i].slotPlus1 = slotPlus1;
+		vol->chunks[items[i].chunkIndex].numVoxelsGpu = n; /* voxel.c:1523 */
+		v->stats.chunksUploaded++;
+		recordBytes += (size_t)n * sizeof(uint4);
+	}
+
+	/* grow the pools before anything is scattered into them (automatic doubling, voxel.c:773-782) */
+	if(v->slotTop > v->slots.cap)
+	{
+		size_t cap = v->slots.cap;
+		while(cap < v->slotTop) cap *= 2;
+		if(!device_reserve(v->slots, cap, true, true, "chunk slots"))
+			return false;
+	}
+	if(v->recordTop > v->records.cap)
+	{
+		size_t cap = v->records.cap;
+		while(cap < v->recordTop) cap *= 2;
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing voxel buffer to accomodate %zu GPU voxels (%zu bytes)", cap, cap * sizeof(uint4));
+		if(!device_reserve(v->records, cap, true, true, "voxel records"))
+			return false;
+		vol->voxelCap = v->records.cap;
+	}
+
+	/* the scatter must not overtake kernels that still read the old chunk contents */
+	cudaStream_t cs = c.stream();
+	cuda_ok(cudaEventRecord(c.evComputeDone, cs), "event record");
+	cuda_ok(cudaStreamWaitEvent(c.uploadStream, c.evComputeDone, 0), "stream wait");
+
+	unsigned char* dBlob = v->blob.ptr;
+	bool ok = cuda_ok(cudaMemcpyAsync(dBlob + offItems, v->pinnedBlob + offItems, offRecords, cudaMemcpyHostToDevice, c.uploadStream), "upload headers");
+	for(unsigned t = 0; t < workers && ok; t++)
+	{
+		if(arenaUsed[t] == 0)
+			continue;
+		const size_t at = offRecords + (count * t / workers) * 512 * sizeof(uint4);
+		ok = cuda_ok(cudaMemcpyAsync(dBlob + at, v->pinnedBlob + at, arenaUsed[t] * sizeof(uint4), cudaMemcpyHostToDevice, c.uploadStream), "upload records");
+	}
+	const uint32_t mapSize[3] = {vol->mapSize.x, vol->mapSize.y, vol->mapSize.z};
+	ok = ok && cuda_ok(dnb_launch_scatter(reinterpret_cast<const DnbUploadItem*>(dBlob + offItems), reinterpret_cast<const DnbSlot*>(dBlob + offHeaders),
+	                                      reinterpret_cast<const uint4*>(dBlob + offRecords), (uint32_t)count, mapSize, v->blocks, v->tileSlot.ptr, v->occ64.ptr, v->visible.ptr,
+	                                      v->slots.ptr, v->records.ptr, c.uploadStream), "scatter kernel");
+
+	v->stats.bytesUploaded += count * (sizeof(DnbUploadItem) + sizeof(DnbSlot)) + recordBytes;
+	return ok;
+}
+
+static void sync_write(VolumeImpl* v)
+{
+	DNvolume* vol = &v->pub;
+	Context& c = ctx();
+	if(v->touched.empty())
+		return;
+
+	ScopedTimer timer(&v->stats.lastUploadMs, c.uploadStream);
+
+	std::vector<PendingItem> pending;
+	pending.reserve(v->touched.size());
+	for(uint32_t tile : v->touched)
+	{
+		v->touchedFlag[tile] = 0;
+		const bool onCpu = vol->map[tile].flag != 0;
+		const bool onGpu = v->tileSlotHost[tile] != 0;
+		PendingItem it;
+		it.tile = tile;
+		it.chunkIndex = vol->map[tile].chunkIndex;
+		it.remove = false;
+		if(onCpu)
+		{
+			DNchunk* chunk = &vol->chunks[it.chunkIndex];
+			if(!onGpu || chunk->updated)
+				pending.push_back(it);
+			chunk->updated = false; /* voxel.c:1534-1535 */
+		}
+		else if(onGpu)
+		{
+			it.remove = true;
+			pending.push_back(it);
+		}
+	}
+	v->touched.clear();
+
+	/* ascending tile order keeps slot / node assignment independent of edit order */
+	std::sort(pending.begin(), pending.end(), [](const PendingItem& a, const PendingItem& b) { return a.tile < b.tile; });
+
+	for(size_t at = 0; at < pending.size(); at += UPLOAD_BATCH)
+		if(!upload_batch(v, pending.data() + at, std::min(UPLOAD_BATCH, pending.size() - at)))
+			break;
+
+	/* later kernels on the compute stream see the new chunks */
+	cuda_ok(cudaEventRecord(c.evUploadDone, c.uploadStream), "event record");
+	cuda_ok(cudaStreamWaitEvent(c.stream(), c.evUploadDone, 0), "stream wait");
+}
+
+/* the reading half: build the request list on the device (compact.cu) */
+static void sync_read(VolumeImpl* v, uint32_t split)
+{
+	DNvolume* vol = &v->pub;
+	Context& c = ctx();
+	cudaStream_t s = c.stream();
+	ScopedTimer timer(&v->stats.lastCompactMs, s);
+
+	DnbScene scene;
+	fill_scene(v, &scene);
+
+	/* chunks with pending edits are lit regardless of the split phase (voxel.c:1470) */
+	const uint32_t* forced = nullptr;
+	if(split > 1)
+	{
+		std::vector<uint32_t> list;
+		for(uint32_t tile : v->touched)
+			if(vol->map[tile].flag != 0 && v->tileSlotHost[tile] != 0 && vol->chunks[vol->map[tile].chunkIndex].updated)
+				list.push_back(tile);
+		if(!list.empty())
+		{
+			device_reserve(v->forcedList, list.size(), false, false, "forced tile list");
+			cuda_ok(cudaMemcpyAsync(v->forcedList.ptr, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s), "forced list upload");
+			cudaStreamSynchronize(s); /* `list` is pageable and about to go out of scope */
+			cuda_ok(dnb_launch_set_bits(v->forced.ptr, v->forcedList.ptr, (uint32_t)list.size(), s), "forced bits");
+			v->forcedDirty = true;
+		}
+		if(v->forcedDirty)
+			forced = v->forced.ptr;
+	}
+
+	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, s), "compaction count");
+	cuda_ok(cudaMemcpyAsync(v->pinnedScalars, v->scalars.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "request count read-back");
+	cuda_ok(cudaStreamSynchronize(s), "compaction count");
+	const size_t total = v->pinnedScalars[0];
+
+	if(total > v->requests.cap)
+	{
+		size_t cap = v->requests.cap ? v->requests.cap : 1024;
+		while(cap < total) cap *= 2;
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing lighting request buffer to accomodate %zu requests (%zu bytes)", cap, cap * sizeof(uint32_t));
+		device_reserve(v->requests, cap, false, false, "lighting requests");
+	}
+	if(total > 0)
+		cuda_ok(dnb_launch_compact_write(&scene, forced, split, vol->frameNum, v->blockOffsets.ptr, v->requests.ptr, s), "compaction write");
+
+	if(forced)
+	{
+		const size_t words = (num_tiles(vol) + 31) / 32;
+		cuda_ok(cudaMemsetAsync(v->forced.ptr, 0, words * sizeof(uint32_t), s), "forced bitmap clear");
+		v->forcedDirty = false;
+	}
+
+	vol->numLightingRequests = total;
+	v->requestsValid = total;
+}
+
+} // namespace dnb
+
+using namespace dnb;
+
+/* ------------------------------------------------------------------------------------------------ */
+
+extern "C" int DN_b200_device_count(void)
+{
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" bool DN_b200_set_device(int ordinal)
+{
+	if(ctx().ready)
+		return false;
+	g_requestedDevice = ordinal;
+	return true;
+}
+
+extern "C" bool DN_init(void)
+{
+	Context& c = ctx();
+	if(c.ready)
+		return true;
+
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if(e != cudaSuccess || count == 0)
+	{
+		cudaGetLastError();
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "no CUDA device available (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+		return false;
+	}
+	int device = g_requestedDevice;
+	if(device < 0)
+	{
+		const char* env = getenv("DN_B200_DEVICE");
+		device = env ? atoi(env) : 0;
+	}
+	if(device < 0 || device >= count || !cuda_ok(cudaSetDevice(device), "cudaSetDevice"))
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "cannot select CUDA device %d of %d", device, count);
+		return false;
+	}
+	c.device = device;
+
+	cudaDeviceProp prop;
+	if(cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties") && prop.major != 10)
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+	bool ok = cuda_ok(cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking), "stream create");
+	ok = ok && cuda_ok(cudaStreamCreateWithFlags(&c.uploadStream, cudaStreamNonBlocking), "stream create");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evUploadDone, cudaEventDisableTiming), "event create");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evComputeDone, cudaEventDisableTiming), "event create");
+	ok = ok && cuda_ok(cudaEventCreate(&c.evT0), "event create") && cuda_ok(cudaEventCreate(&c.evT1), "event create");
+	if(!ok)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "failed to create CUDA streams");
+		return false;
+	}
+
+	/* sRGB -> linear, truncated, with the reference's constants and libm powf (voxel.c:1441-1447) */
+	for(int i = 0; i < 256; i++)
+	{
+		float f = (float)i * 0.00392156862f;
+		f = powf(f, DN_GAMMA);
+		f = f * 255.0f;
+		c.albedoLut[i] = (uint8_t)f;
+	}
+
+	c.framebuffers.clear();
+	c.framebuffers.resize(1); /* handle 0 is never valid */
+	c.ready = true;
+	return true;
+}
+
+extern "C" void DN_quit(void)
+{
+	Context& c = ctx();
+	if(!c.ready)
+		return;
+	cudaStreamSynchronize(c.ownStream);
+	cudaStreamSynchronize(c.uploadStream);
+	for(Framebuffer& fb : c.framebuffers)
+	{
+		if(fb.image) cudaFree(fb.image);
+		if(fb.hits) cudaFree(fb.hits);
+	}
+	c.framebuffers.clear();
+	cudaEventDestroy(c.evUploadDone); cudaEventDestroy(c.evComputeDone); cudaEventDestroy(c.evT0); cudaEventDestroy(c.evT1);
+	cudaStreamDestroy(c.ownStream);
+	cudaStreamDestroy(c.uploadStream);
+	c.ownStream = c.uploadStream = nullptr;
+	c.ready = false;
+}
+
+extern "C" void DN_b200_set_stream(void* cudaStream)
+{
+	Context& c = ctx();
+	if(c.ready)
+		cudaStreamSynchronize(c.stream());
+	c.userStream = (cudaStream_t)cudaStream;
+	c.useUserStream = cudaStream != nullptr;
+}
+
+extern "C" bool DN_b200_synchronize(void)
+{
+	Context& c = ctx();
+	if(!c.ready)
+		return false;
+	bool ok = cuda_ok(cudaStreamSynchronize(c.uploadStream), "synchronize (upload stream)");
+	return cuda_ok(cudaStreamSynchronize(c.stream()), "synchronize") && ok;
+}
+
+extern "C" void DN_b200_enable_timing(bool enable) { ctx().timing = enable; }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* framebuffers                                                                                       */
+
+static Framebuffer* find_fb(GLuint id)
+{
+	Context& c = ctx();
+	if(id == 0 || id >= c.framebuffers.size() || !c.framebuffers[id].used)
+		return nullptr;
+	return &c.framebuffers[id];
+}
+
+extern "C" GLuint DN_b200_create_framebuffer(int width, int height)
+{
+	Context& c = ctx();
+	if(!c.ready || width <= 0 || height <= 0)
+		return 0;
+	Framebuffer fb;
+	fb.used = true;
+	fb.width = width;
+	fb.height = height;
+	if(!cuda_ok(cudaMalloc((void**)&fb.image, (size_t)width * height * sizeof(float4)), "framebuffer"))
+		return 0;
+	cudaMemsetAsync(fb.image, 0, (size_t)width * height * sizeof(float4), c.stream());
+	for(size_t i = 1; i < c.framebuffers.size(); i++)
+		if(!c.framebuffers[i].used)
+		{
+			c.framebuffers[i] = fb;
+			return (GLuint)i;
+		}
+	c.framebuffers.push_back(fb);
+	return (GLuint)(c.framebuffers.size() - 1);
+}
+
+extern "C" void DN_b200_delete_framebuffer(GLuint id)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb)
+		return;
+	cudaStreamSynchronize(ctx().stream());
+	cudaFree(fb->image);
+	if(fb->hits) cudaFree(fb->hits);
+	*fb = Framebuffer();
+}
+
+extern "C" bool DN_b200_framebuffer_size(GLuint id, int* width, int* height)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb)
+		return false;
+	*width = fb->width;
+	*height = fb->height;
+	return true;
+}
+
+extern "C" void* DN_b200_framebuffer_device_ptr(GLuint id)
+{
+	Framebuffer* fb = find_fb(id);
+	return fb ? fb->image : nullptr;
+}
+
+extern "C" bool DN_b200_read_framebuffer(GLuint id, float* dst, size_t bytes)
+{
+	Framebuffer* fb = find_fb(id);
+	const size_t need = fb ? (size_t)fb->width * fb->height * sizeof(float4) : 0;
+	if(!fb || bytes < need)
+		return false;
+	cudaStream_t s = ctx().stream();
+	return cuda_ok(cudaMemcpyAsync(dst, fb->image, need, cudaMemcpyDeviceToHost, s), "framebuffer read") && cuda_ok(cudaStreamSynchronize(s), "framebuffer read");
+}
+
+extern "C" bool DN_b200_clear_framebuffer(GLuint id, float value)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb)
+		return false;
+	/* only 0 and bit patterns made of one repeated byte can be memset; everything else goes through the host */
+	if(value == 0.0f)
+		return cuda_ok(cudaMemsetAsync(fb->image, 0, (size_t)fb->width * fb->height * sizeof(float4), ctx().stream()), "framebuffer clear");
+	std::vector<float> fill((size_t)fb->width * fb->height * 4, value);
+	return cuda_ok(cudaMemcpy(fb->image, fill.data(), fill.size() * sizeof(float), cudaMemcpyHostToDevice), "framebuffer clear");
+}
+
+extern "C" bool DN_b200_capture_hits(GLuint id, bool enable)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb)
+		return false;
+	if(enable && !fb->hits)
+	{
+		if(!cuda_ok(cudaMalloc((void**)&fb->hits, (size_t)fb->width * fb->height * sizeof(DnbHit)), "hit buffer"))
+			return false;
+		cudaMemsetAsync(fb->hits, 0, (size_t)fb->width * fb->height * sizeof(DnbHit), ctx().stream());
+	}
+	else if(!enable && fb->hits)
+	{
+		cudaStreamSynchronize(ctx().stream());
+		cudaFree(fb->hits);
+		fb->hits = nullptr;
+	}
+	return true;
+}
+
+extern "C" bool DN_b200_read_hits(GLuint id, DNb200hit* dst, size_t count)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb || !fb->hits || count < (size_t)fb->width * fb->height)
+		return false;
+	cudaStream_t s = ctx().stream();
+	return cuda_ok(cudaMemcpyAsync(dst, fb->hits, (size_t)fb->width * fb->height * sizeof(DnbHit), cudaMemcpyDeviceToHost, s), "hit read") && cuda_ok(cudaStreamSynchronize(s), "hit read");
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* frame                                                                                              */
+
+/* every frame entry point refuses to run without device state: there is no CPU path to fall back to */
+static bool device_ready(VolumeImpl* v, const char* who)
+{
+	if(ctx().ready && v->tileSlot.ptr)
+		return true;
+	report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "%s: no CUDA device state (DN_init failed or was not called); this library has no CPU path", who);
+	return false;
+}
+
+extern "C" void DN_sync_gpu(DNvolume* vol, DNmemOp op, int lightingSplit)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_sync_gpu"))
+		return;
+	if(lightingSplit < 1)
+		lightingSplit = 1;
+
+	/* voxel.c:725-727 */
+	vol->frameNum++;
+	if(vol->frameNum >= (uint32_t)lightingSplit)
+		vol->frameNum = 0;
+	vol->numLightingRequests = 0;
+	v->requestsValid = 0;
+
+	/* requests first: they are sized from what is resident BEFORE this call's uploads (voxel.c:757 precedes :761) */
+	if(op != DN_WRITE)
+		sync_read(v, (uint32_t)lightingSplit);
+	if(op != DN_READ)
+		sync_write(v);
+}
+
+extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4 projection, int rasterColorTexture, int rasterDepthTexture)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_draw"))
+		return;
+	Framebuffer* fb = find_fb(outputTexture);
+	if(!fb)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_draw: %u is not a framebuffer created by DN_b200_create_framebuffer", outputTexture);
+		return;
+	}
+	if(rasterColorTexture >= 0 && rasterDepthTexture >= 0)
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_draw: composing with rasterized objects is not supported by the CUDA back end; drawing voxels only");
+	if(vol->useCubemap)
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_draw: cubemap skies are not supported by the CUDA back end; using the sky gradient");
+
+	cudaStream_t s = ctx().stream();
+	ScopedTimer timer(&v->stats.lastDrawMs, s);
+
+	/* materials travel with every draw, as upstream (voxel.c:823-824) */
+	cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
+
+	/* voxel.c:845-853 */
+	Mat4 V, P, C;
+	memcpy(V.m, view.m, sizeof(V.m));
+	memcpy(P.m, projection.m, sizeof(P.m));
+	C = V;
+	C.m[3][0] = 0.0f; C.m[3][1] = 0.0f; C.m[3][2] = 0.0f;
+	const Mat4 invV = inverse(V), invC = inverse(C), invP = inverse(P);
+
+	DnbScene scene;
+	fill_scene(v, &scene);
+	DnbDrawParams dp;
+	memcpy(dp.invView, invV.m, 64);
+	memcpy(dp.invCenteredView, invC.m, 64);
+	memcpy(dp.invProjection, invP.m, 64);
+	dp.viewMode = vol->camViewMode;
+	dp.width = fb->width;
+	dp.height = fb->height;
+	const int groupRows = fb->height / 16;
+	if(v->shardWorld > 1)
+	{
+		const int per = (groupRows + v->shardWorld - 1) / v->shardWorld;
+		dp.rowBegin = std::min(groupRows, per * v->shardRank);
+		dp.rowEnd = std::min(groupRows, per * (v->shardRank + 1));
+	}
+	else
+	{
+		dp.rowBegin = 0;
+		dp.rowEnd = groupRows;
+	}
+	cuda_ok(dnb_launch_draw(&scene, &dp, fb->image, fb->hits, s), "draw kernel");
+}
+
+static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSamples, float time)
+{
+	DNvolume* vol = &v->pub;
+	if(!device_ready(v, "DN_update_lighting"))
+		return false;
+	cudaStream_t s = ctx().stream();
+
+	/* voxel.c:886-887 */
+	if(vol->frameNum == 0)
+		vol->lastTime = time;
+
+	const size_t total = v->requestsValid;
+	v->stagedRequests = total;
+	if(total == 0)
+		return true;
+
+	if(numDiffuseSamples < 0) numDiffuseSamples = 0;
+	if(numDiffuseSamples > DNB_MAX_SAMPLES || vol->diffuseBounceLimit > DNB_MAX_BOUNCES)
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_update_lighting: at most %d diffuse samples and %d diffuse bounces per dispatch are supported; clamping", DNB_MAX_SAMPLES, DNB_MAX_BOUNCES);
+
+	DnbLightParams lp;
+	memset(&lp, 0, sizeof(lp));
+	memcpy(lp.camPos, &vol->camPos, 12);
+	float sun[3] = {vol->sunDir.x, vol->sunDir.y, vol->sunDir.z};
+	normalize(sun); /* voxel.c:942 */
+	memcpy(lp.sunDir, sun, 12);
+	lp.shadowSoftness = vol->shadowSoftness;
+	lp.time = vol->lastTime;
+	lp.numDiffuseSamples = (uint32_t)std::min(numDiffuseSamples, (int)DNB_MAX_SAMPLES);
+	lp.maxDiffuseSamples = (uint32_t)maxDiffuseSamples;
+	lp.diffuseBounceLimit = std::min<uint32_t>(vol->diffuseBounceLimit, DNB_MAX_BOUNCES);
+	lp.specularBounceLimit = vol->specBounceLimit;
+
+	/* every random number of the dispatch (layout.h DnbLightParams).  NOTE the seeds use the UNclamped uniforms,
+	 * exactly as the shader would form them. */
+	const float t = lp.time;
+	const float fLimit = (float)vol->diffuseBounceLimit;
+	for(uint32_t i = 0; i < lp.numDiffuseSamples; i++)
+	{
+		const float seed = t * (float)(i + 1);                                  /* LI:259 */
+		for(uint32_t b = 0; b < lp.diffuseBounceLimit; b++)
+		{
+			lp.glossyChoice[i][b] = (shader_rand(seed + fLimit + (float)b) + 1.0f) * 0.5f; /* LI:162 */
+			shader_rand_unit_sphere(seed + (float)b, lp.diffuseBall[i][b]);           /* LI:168 */
+		}
+		shader_rand_unit_sphere(t * (float)(i + 1 + (uint32_t)numDiffuseSamples), lp.shadowBall[i]); /* LI:260,75 */
+	}
+	for(uint32_t b = 0; b < lp.diffuseBounceLimit; b++)
+		shader_rand_unit_sphere(t + (float)b, lp.glossyBall[b]);                    /* LI:163 */
+
+	DnbScene scene;
+	fill_scene(v, &scene);
+
+	/* slice of the request list this process lights */
+	size_t first = 0, count = total, paddedTotal = total;
+	if(v->shardWorld > 1)
+	{
+		const size_t per = (total + v->shardWorld - 1) / v->shardWorld;
+		first = std::min(total, per * (size_t)v->shardRank);
+		count = std::min(total, per * (size_t)(v->shardRank + 1)) - first;
+		paddedTotal = per * (size_t)v->shardWorld;
+	}
+	if(!device_reserve(v->staging, paddedTotal * 96, false, false, "lighting staging"))
+		return false;
+
+	ScopedTimer timer(&v->stats.lastLightMs, s);
+	bool ok = cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
+	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
+	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, (uint32_t)first, (uint32_t)count, v->staging.ptr, s), "lighting kernel");
+	return ok;
+}
+
+static bool light_commit(VolumeImpl* v)
+{
+	if(!device_ready(v, "DN_b200_light_commit"))
+		return false;
+	cudaStream_t s = ctx().stream();
+	DnbScene scene;
+	fill_scene(v, &scene);
+	ScopedTimer timer(&v->stats.lastCommitMs, s);
+	return cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, (uint32_t)v->stagedRequests, v->staging.ptr, s), "commit kernel");
+}
+
+extern "C" void DN_update_lighting(DNvolume* vol, int numDiffuseSamples, int maxDiffuseSamples, float time)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(v->shardWorld > 1)
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_update_lighting on a sharded volume lights only this rank's slice; use DN_b200_light_compute + all-gather + DN_b200_light_commit");
+	if(light_compute(v, numDiffuseSamples, maxDiffuseSamples, time))
+		light_commit(v);
+}
+
+extern "C" bool DN_b200_light_compute(DNvolume* vol, int numDiffuseSamples, int maxDiffuseSamples, float time)
+{
+	return light_compute(impl_of(vol), numDiffuseSamples, maxDiffuseSamples, time);
+}
+
+extern "C" bool DN_b200_light_commit(DNvolume* vol)
+{
+	return light_commit(impl_of(vol));
+}
+
+extern "C" size_t DN_b200_staging_slice_bytes(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	const size_t per = (v->stagedRequests + v->shardWorld - 1) / v->shardWorld;
+	return per * 96 * sizeof(uint32_t);
+}
+
+extern "C" bool DN_b200_set_shard(DNvolume* vol, int rank, int worldSize)
+{
+	if(worldSize < 1 || rank < 0 || rank >= worldSize)
+		return false;
+	VolumeImpl* v = impl_of(vol);
+	v->shardRank = rank;
+	v->shardWorld = worldSize;
+	return true;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* capacity of the record pool: voxel.c:1031-1082                                                     */
+
+extern "C" bool DN_set_max_voxels_gpu(DNvolume* vol, size_t num)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_set_max_voxels_gpu"))
+		return false;
+	if(num < v->recordTop)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_set_max_voxels_gpu: %zu records are in use, cannot shrink to %zu", v->recordTop, num);
+		return false;
+	}
+	if(num <= v->records.cap)
+		return true; /* never shrinks: resident records keep their place */
+	if(!device_reserve(v->records, num, true, true, "voxel records"))
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "failed to reallocate voxel buffer");
+		return false;
+	}
+	vol->voxelCap = v->records.cap;
+	return true;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* state access                                                                                       */
+
+static bool array_info(VolumeImpl* v, DNb200array which, void** ptr, size_t* bytes)
+{
+	const size_t tiles = num_tiles(&v->pub);
+	switch(which)
+	{
+	case DN_B200_TILE_SLOTS: *ptr = v->tileSlot.ptr; *bytes = tiles * sizeof(uint32_t); return true;
+	case DN_B200_VISIBLE:    *ptr = v->visible.ptr;  *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
+	case DN_B200_SLOTS:      *ptr = v->slots.ptr;    *bytes = (size_t)v->slotTop * sizeof(DnbSlot); return true;
+	case DN_B200_RECORDS:    *ptr = v->records.ptr;  *bytes = v->recordTop * sizeof(uint4); return true;
+	case DN_B200_REQUESTS:   *ptr = v->requests.ptr; *bytes = v->requestsValid * sizeof(uint32_t); return true;
+	case DN_B200_STAGING:
+	{
+		const size_t per = (v->stagedRequests + v->shardWorld - 1) / v->shardWorld;
+		*ptr = v->staging.ptr;
+		*bytes = per * v->shardWorld * 96 * sizeof(uint32_t);
+		return true;
+	}
+	}
+	return false;
+}
+
+extern "C" size_t DN_b200_array_bytes(DNvolume* vol, DNb200array which)
+{
+	void* p;
+	size_t n;
+	return array_info(impl_of(vol), which, &p, &n) ? n : 0;
+}
+
+extern "C" void* DN_b200_array_device_ptr(DNvolume* vol, DNb200array which)
+{
+	void* p;
+	size_t n;
+	return array_info(impl_of(vol), which, &p, &n) ? p : nullptr;
+}
+
+extern "C" size_t DN_b200_download(DNvolume* vol, DNb200array which, void* dst, size_t dstBytes)
+{
+	void* p;
+	size_t n;
+	if(!ctx().ready || !array_info(impl_of(vol), which, &p, &n) || n > dstBytes)
+		return 0;
+	if(n == 0 || !p)
+		return 0;
+	if(!DN_b200_synchronize())
+		return 0;
+	if(!cuda_ok(cudaMemcpy(dst, p, n, cudaMemcpyDeviceToHost), "download"))
+		return 0;
+	return n;
+}
+
+extern "C" size_t DN_b200_fetch_lighting_requests(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	const size_t total = v->requestsValid;
+	if(total > vol->lightingRequestCap)
+	{
+		size_t cap = vol->lightingRequestCap ? vol->lightingRequestCap : 1;
+		while(cap < total) cap *= 2;
+		report(DN_MESSAGE_CPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing lighting request memory to accomodate %zu requests (%zu bytes)", cap, cap * sizeof(GLuint));
+		if(!DN_set_max_lighting_requests(vol, cap))
+			return 0;
+	}
+	if(total && DN_b200_download(vol, DN_B200_REQUESTS, vol->lightingRequests, vol->lightingRequestCap * sizeof(GLuint)) == 0)
+		return 0;
+	return total;
+}
+
+extern "C" bool DN_b200_enable_counters(DNvolume* vol, bool enable)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!ctx().ready)
+		return false;
+	if(enable && !v->counters)
+	{
+		if(!cuda_ok(cudaMalloc((void**)&v->counters, sizeof(DnbCounters)), "counters"))
+			return false;
+		cudaMemsetAsync(v->counters, 0, sizeof(DnbCounters), ctx().stream());
+	}
+	else if(!enable && v->counters)
+	{
+		DN_b200_synchronize();
+		cudaFree(v->counters);
+		v->counters = nullptr;
+	}
+	return true;
+}
+
+extern "C" bool DN_b200_read_counters(DNvolume* vol, DNb200counters* out, bool reset)
+{
+	VolumeImpl* v = impl_of(vol);
+	memset(out, 0, sizeof(*out));
+	if(!v->counters || !DN_b200_synchronize())
+		return false;
+	DnbCounters h;
+	if(!cuda_ok(cudaMemcpy(&h, v->counters, sizeof(h), cudaMemcpyDeviceToHost), "counter read"))
+		return false;
+	out->rays = h.rays; out->tiles = h.tiles; out->chunks = h.chunks; out->voxelSteps = h.voxelSteps;
+	out->records = h.records; out->voxelsLit = h.voxelsLit; out->pixels = h.pixels;
+	if(reset)
+		cudaMemset(v->counters, 0, sizeof(DnbCounters));
+	return true;
+}
+
+extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
+{
+	VolumeImpl* v = impl_of(vol);
+	v->stats.slotCap = v->slots.cap;
+	v->stats.recordCap = v->records.cap;
+	*out = v->stats;
+}
+
+extern "C" cudaError_t dnb_launch_or_bits(uint32_t* dst, const uint32_t* src, uint32_t words, cudaStream_t stream);
+
+extern "C" bool DN_b200_or_visible(DNvolume* vol, const void* deviceBitmap)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_b200_or_visible"))
+		return false;
+	const uint32_t words = (uint32_t)((num_tiles(vol) + 31) / 32);
+	return cuda_ok(dnb_launch_or_bits(v->visible.ptr, (const uint32_t*)deviceBitmap, words, ctx().stream()), "visible merge");
+}

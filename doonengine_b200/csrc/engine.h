@@ -1,0 +1,112 @@
+/* engine.h -- private state behind a DNvolume and the process-wide CUDA context. */
+#ifndef DN_B200_ENGINE_H
+#define DN_B200_ENGINE_H
+
+#include "DoonEngine/b200.h"
+#include "DoonEngine/voxel.h"
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <vector>
+
+namespace dnb
+{
+
+/* size classes of the record pool: 16, 32, 64, 128, 256, 512 records (same node sizes as voxel.c:1557-1559) */
+enum { NUM_NODE_CLASSES = 6 };
+
+template <typename T> struct DeviceArray
+{
+	T*     ptr = nullptr;
+	size_t cap = 0; /* elements */
+};
+
+struct Framebuffer
+{
+	bool    used = false;
+	int     width = 0, height = 0;
+	float4* image = nullptr;
+	DnbHit* hits = nullptr;
+};
+
+struct Context
+{
+	bool         ready = false;
+	int          device = 0;
+	cudaStream_t ownStream = nullptr;    /* kernels */
+	cudaStream_t uploadStream = nullptr; /* host->device copies of edited chunks + their scatter */
+	cudaStream_t userStream = nullptr;   /* DN_b200_set_stream */
+	bool         useUserStream = false;
+	cudaEvent_t  evUploadDone = nullptr, evComputeDone = nullptr;
+	cudaEvent_t  evT0 = nullptr, evT1 = nullptr;
+	bool         timing = false;
+	uint8_t      albedoLut[256];         /* trunc(255 * (a * 0.00392156862)^2.2), voxel.c:1441-1447 */
+	std::vector<Framebuffer> framebuffers;
+
+	cudaStream_t stream() const { return useUserStream ? userStream : ownStream; }
+};
+
+Context& ctx();
+
+/* the public struct comes first so that DNvolume* == VolumeImpl* */
+struct VolumeImpl
+{
+	DNvolume pub;
+	uint32_t magic;
+
+	/* ---- host mirror of what is resident ---- */
+	std::vector<uint32_t> tileSlotHost;   /* per tile: 0 or slot+1 */
+	std::vector<uint32_t> freeSlots;
+	uint32_t              slotTop = 0;    /* slots [0, slotTop) have been handed out at least once */
+	std::vector<uint32_t> slotNodeStart;  /* per slot: first record of its node */
+	std::vector<uint8_t>  slotNodeClass;  /* per slot: size class of its node, 0xFF = none */
+	std::vector<uint32_t> slotNumVoxels;  /* per slot: records in use */
+	std::vector<uint32_t> freeNodes[NUM_NODE_CLASSES];
+	size_t                recordTop = 0;  /* bump pointer of the record pool */
+
+	/* ---- edit tracking ---- */
+	std::vector<uint32_t> touched;        /* tiles to reconcile at the next writing sync */
+	std::vector<uint8_t>  touchedFlag;
+
+	/* ---- device ---- */
+	uint32_t blocks[3];
+	DeviceArray<uint32_t>           tileSlot;
+	DeviceArray<unsigned long long> occ64;
+	DeviceArray<uint32_t>           visible, propagate, forced;
+	DeviceArray<DnbSlot>            slots;
+	DeviceArray<uint4>              records;
+	DeviceArray<DnbMaterial>        materials;
+	DeviceArray<uint32_t>           requests;
+	DeviceArray<uint32_t>           staging;   /* 96 words per request */
+	DeviceArray<uint32_t>           blockCounts, blockOffsets, scalars;
+	DeviceArray<uint32_t>           forcedList;
+	DeviceArray<unsigned char>      blob;      /* device side of the upload batch */
+	unsigned char* pinnedBlob = nullptr;
+	size_t         pinnedBlobCap = 0;
+	uint32_t*      pinnedScalars = nullptr;    /* read-back of the request count */
+	DnbCounters*   counters = nullptr;         /* device, NULL when instrumentation is off */
+	bool           forcedDirty = false;
+
+	size_t requestsValid = 0;                  /* requests on the device from the last reading sync */
+	size_t stagedRequests = 0;                 /* requests covered by the staging array (last compute phase) */
+	int    shardRank = 0, shardWorld = 1;
+
+	DNb200stats stats;
+};
+
+const uint32_t VOLUME_MAGIC = 0xD00EB200u;
+
+void report(DNmessageType type, DNmessageSeverity severity, const char* fmt, ...);
+bool cuda_ok(cudaError_t e, const char* what);
+
+inline VolumeImpl* impl_of(DNvolume* vol) { return reinterpret_cast<VolumeImpl*>(vol); }
+inline size_t      num_tiles(const DNvolume* vol) { return (size_t)vol->mapSize.x * vol->mapSize.y * vol->mapSize.z; }
+
+void touch_tile(VolumeImpl* v, size_t mapIndex);
+bool device_create(VolumeImpl* v);   /* allocates the per-tile arrays for pub.mapSize */
+void device_destroy(VolumeImpl* v);
+void fill_scene(VolumeImpl* v, DnbScene* s);
+
+} // namespace dnb
+
+#endif

@@ -1,0 +1,40 @@
+/* kernels.h -- launch wrappers of the CUDA kernels (draw.cu, light.cu, compact.cu, upload.cu). */
+#ifndef DN_B200_KERNELS_H
+#define DN_B200_KERNELS_H
+
+#include "layout.h"
+#include <cuda_runtime.h>
+
+/* one edited chunk in an upload batch (upload.cu) */
+typedef struct DnbUploadItem
+{
+	uint32_t mapIndex;
+	uint32_t slotPlus1;    /* 0 = the tile lost its chunk */
+	uint32_t recordOffset; /* first record of this chunk inside the batch's record blob */
+	uint32_t pad;
+} DnbUploadItem;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, DnbHit* hits, cudaStream_t stream);
+
+cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream);
+cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* staging, cudaStream_t stream);
+cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging, cudaStream_t stream);
+
+uint32_t    dnb_compact_num_blocks(uint32_t numTiles);
+cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets, uint32_t* grandTotal,
+                                     cudaStream_t stream);
+cudaError_t dnb_launch_compact_write(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, const uint32_t* blockOffsets, uint32_t* requests, cudaStream_t stream);
+cudaError_t dnb_launch_set_bits(uint32_t* bits, const uint32_t* tiles, uint32_t n, cudaStream_t stream);
+
+cudaError_t dnb_launch_scatter(const DnbUploadItem* items, const DnbSlot* headers, const uint4* blobRecords, uint32_t numItems, const uint32_t mapSize[3], const uint32_t blocks[3],
+                               uint32_t* tileSlot, unsigned long long* occ64, uint32_t* visible, DnbSlot* slots, uint4* records, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,390 @@
+/* light.cu -- the per-voxel lighting update, in two phases so that it is deterministic and shardable.
+ *
+ * Phase 1  dn_light_kernel   one warp per lighting request (= 32 consecutive surface voxels of one chunk,
+ *                            voxelLighting.comp:3,212-214), one thread per voxel.  Traces the 15 fixed
+ *                            specular rays, the diffuse paths and the shadow rays (LI:65-203,224-264),
+ *                            forms the running mean and packs the three lighting words (LI:266-278) into a
+ *                            STAGING buffer in request order.  It reads the map strictly read-only, so every
+ *                            ray sees the pre-dispatch lighting (oracle.h N1/N2) and a slice of the request
+ *                            list can run on any GPU.
+ * Phase 2  dn_commit_kernel  scatters the staged words into the voxel records (coalesced 16-byte stores),
+ *                            clears the visible bit of every chunk that had a live invocation (LI:281) and
+ *                            bumps the chunk's sample count once (LI:284-285).
+ *          dn_merge_visible_kernel  ORs in the visible bits raised by specular hits (LI:101-105) after the
+ *                            clears (N3).
+ *
+ * Staging layout: request r owns 96 words: [32 x w1][32 x w2][32 x w3] -> three fully coalesced 128-byte
+ * stores per warp, and a contiguous byte range per rank for the multi-GPU all-gather.
+ */
+#include "kernels.h"
+#include "trace.cuh"
+
+/* LI:23 */
+__constant__ float c_spherePoints[15][3] = {
+	{0.000000f, 1.000000f, 0.000000f}, {-0.379803f, 0.857143f, 0.347931f}, {0.061185f, 0.714286f, -0.697174f},
+	{0.499316f, 0.571429f, 0.651270f}, {-0.889696f, 0.428571f, -0.157375f}, {0.808584f, 0.285714f, -0.514354f},
+	{-0.256942f, 0.142857f, 0.955810f}, {-0.460906f, 0.000000f, -0.887449f}, {0.929687f, -0.142857f, 0.339521f},
+	{-0.885815f, -0.285714f, 0.365650f}, {0.382949f, -0.428571f, -0.818338f}, {0.245607f, -0.571429f, 0.783037f},
+	{-0.605521f, -0.714286f, -0.350913f}, {0.503065f, -0.857143f, -0.110596f}, {-0.000000f, -1.000000f, 0.000000f}};
+
+/* per-dispatch parameters incl. the host-evaluated random table (layout.h) */
+__constant__ DnbLightParams c_light;
+
+struct LightCtx
+{
+	RayState    st;
+	DnbCounters lc;
+	bool        firstSample;    /* LI:62 */
+	bool        sourceVisible;  /* visible bit of the chunk being lit, pre-dispatch (N3) */
+};
+
+DNB_FN uint32_t encode_rgba(uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+	return ((x & 0xFFu) << 24) | ((y & 0xFFu) << 16) | ((z & 0xFFu) << 8) | (w & 0xFFu);
+}
+
+/* LI:65-80 */
+template <bool COUNT>
+DNB_FN void shadow_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, uint32_t sample, f3& color)
+{
+	const f3 sunDir = ld3(c_light.sunDir);
+	f3 dir;
+	if(cx.firstSample)
+		dir = sunDir + DNB_EPSILON;
+	else
+		dir = normalize3(sunDir * c_light.shadowSoftness + ld3(c_light.shadowBall[sample])) + DNB_EPSILON;
+
+	f3 tmpNormal = splat3(0.0f), colorAdd;
+	float colorMult;
+	if(!trace_ray<false, COUNT>(S, cx.st, cx.lc, dir, rcp3(dir), rayPos, true, tmpNormal, colorAdd, colorMult))
+		color = color + (ld3(S.sunStrength) * colorMult + colorAdd);
+}
+
+/* LI:83-146 */
+template <bool COUNT>
+DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, f3 albedo, uint32_t reflectType, f3& color)
+{
+	f3 lastPos = rayPos;
+	f3 multiplier = albedo;
+	const f3 sunDir = ld3(c_light.sunDir);
+
+	for(uint32_t i = 0; i < c_light.specularBounceLimit; i++)
+	{
+		f3 colorAdd, tmpNormal = splat3(0.0f);
+		float colorMult;
+		if(trace_ray<false, COUNT>(S, cx.st, cx.lc, rayDir, rcp3(rayDir), rayPos, true, tmpNormal, colorAdd, colorMult))
+		{
+			/* LI:101-105: a visible chunk makes the chunks it reflects visible */
+			i3 hp = toi3(rayPos);
+			if(cx.sourceVisible && in_map_bounds(S, hp))
+			{
+				uint32_t hitIndex = (uint32_t)hp.x + S.mapSize[0] * ((uint32_t)hp.y + S.mapSize[1] * (uint32_t)hp.z);
+				uint32_t bit = 1u << (hitIndex & 31u);
+				if(!(__ldcg(S.propagate + (hitIndex >> 5)) & bit))
+					atomicOr(S.propagate + (hitIndex >> 5), bit);
+			}
+
+			/* LI:108-110: adjacent hit = occluded */
+			f3 dist = abs3(floor3(rayPos * 8.0f) - floor3(lastPos * 8.0f));
+			if(dot3(dist, dist) <= 1.0f)
+				return;
+
+			const uint4 rec = cx.st.vox;
+			DnbMaterial hitMaterial = load_material(S, vox_material(rec));
+			f3 hitAlbedo = vox_albedo(rec);
+			f3 hitDiffuse = vox_diffuse(rec) * (1.0f - hitMaterial.specular);
+
+			if(hitMaterial.emissive)
+			{
+				color = color + ((hitAlbedo * colorMult + colorAdd) * multiplier) * albedo;
+				return;
+			}
+
+			f3 hitColor = hitDiffuse * hitAlbedo;
+			color = color + (hitColor * colorMult + colorAdd) * multiplier;
+			if(hitMaterial.specular == 0.0f)
+				return;
+
+			multiplier = multiplier * ((hitAlbedo * colorMult) * hitMaterial.specular);
+			reflectType = hitMaterial.reflectType;
+			lastPos = rayPos;
+			rayDir = reflect3(rayDir, vox_normal(rec));
+		}
+		else if(dot3(rayDir, sunDir) > 0.99f)
+		{
+			color = color + (ld3(S.sunStrength) * colorMult + colorAdd);
+			return;
+		}
+		else
+		{
+			f3 base = (reflectType == 1u) ? sky_color(S, rayDir) : ld3(S.sunStrength);
+			color = color + (base * colorMult + colorAdd) * multiplier;
+			return;
+		}
+	}
+}
+
+/* LI:149-203 */
+template <bool COUNT>
+DNB_FN void diffuse_ray(const DnbScene& S, LightCtx& cx, f3 normal, f3 rayPos, uint4 initialVoxel, uint32_t sample, f3& color)
+{
+	cx.st.vox = initialVoxel;
+	f3 hitNormal = normal;
+	DnbMaterial hitMaterial;
+	hitMaterial.specular = 0.0f;
+	hitMaterial.shininess = 0;
+	hitMaterial.emissive = 0;
+
+	f3 newColor = splat3(1.0f);
+	const f3 lastPos = rayPos; /* never advanced: adjacency is tested against the first origin (LI:157,182) */
+	f3 lastDir = splat3(0.0f);
+	const f3 sunDir = ld3(c_light.sunDir);
+
+	for(uint32_t i = 0; i < c_light.diffuseBounceLimit; i++)
+	{
+		f3 dir;
+		if(i > 0 && c_light.glossyChoice[sample][i] < hitMaterial.specular)
+			dir = normalize3(reflect3(lastDir, hitNormal) * (float)hitMaterial.shininess + ld3(c_light.glossyBall[i]));
+		else if(cx.firstSample)
+			dir = normalize3(hitNormal) + DNB_EPSILON;
+		else
+			dir = normalize3(hitNormal + ld3(c_light.diffuseBall[sample][i])) + DNB_EPSILON;
+
+		f3 colorAdd, tmpNormal = splat3(0.0f);
+		float colorMult;
+		bool hit = trace_ray<false, COUNT>(S, cx.st, cx.lc, dir, rcp3(dir), rayPos, true, tmpNormal, colorAdd, colorMult);
+
+		const uint4 rec = cx.st.vox;
+		hitNormal = vox_normal(rec);
+		hitMaterial = load_material(S, vox_material(rec));
+
+		if(hit)
+		{
+			f3 dist = abs3(floor3(lastPos * 8.0f) - floor3(rayPos * 8.0f));
+			if(dot3(dist, dist) < 1.0f)
+				return;
+
+			f3 through = vox_albedo(rec) * colorMult + colorAdd;
+			if(hitMaterial.emissive)
+			{
+				color = color + newColor * through;
+				return;
+			}
+			newColor = newColor * through;
+		}
+		else
+		{
+			float ndl = fmaxf(dot3(dir, sunDir), 0.0f);
+			color = color + (((newColor * ndl) * ld3(S.sunStrength)) * colorMult + colorAdd);
+			return;
+		}
+
+		lastDir = dir;
+	}
+}
+
+/* n-th set bit of the 512-bit mask -> local voxel index (same answer as get_voxel_position, SH:172-224,
+ * whose `<` partial-count quirk only changes where its scan starts) */
+DNB_FN int nth_voxel(const uint32_t* mask, const uint16_t* prefix, uint32_t numVoxels, uint32_t voxNum)
+{
+	if(voxNum >= numVoxels)
+		return -1;
+	int w = 0;
+#pragma unroll
+	for(int i = 1; i < 16; i++)
+		if((uint32_t)prefix[i] <= voxNum)
+			w = i;
+	/* prefix is non-decreasing, so w is the last word starting at or before voxNum; skip empty words backwards is not
+	 * needed: the word containing the voxel is the last one whose prefix <= voxNum AND has a bit there */
+	uint32_t inWord = voxNum - (uint32_t)prefix[w];
+	return w * 32 + (int)__fns(mask[w], 0, (int)inWord + 1);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* __restrict__ staging)
+{
+	__shared__ DnbSlot s_slot[4];
+
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t r = firstRequest + blockIdx.x * 4 + warp;
+	if(r >= firstRequest + numRequests)
+		return;
+
+	const uint32_t request = __ldg(requests + r);
+	const uint32_t mapIndex = request >> 4;
+	uint32_t* out = staging + (size_t)r * 96u;
+
+	const uint32_t slotId = __ldg(S.tileSlot + mapIndex) - 1u;
+	if(slotId == 0xFFFFFFFFu)
+	{
+		/* the chunk was removed between the request and the dispatch: nothing to light */
+		out[lane] = 0; out[32 + lane] = 0; out[64 + lane] = 0;
+		return;
+	}
+
+	/* stage the 128-byte chunk slot: one coalesced load per warp */
+	reinterpret_cast<uint32_t*>(&s_slot[warp])[lane] = __ldg(reinterpret_cast<const uint32_t*>(S.slots + slotId) + lane);
+	__syncwarp();
+	const DnbSlot& slot = s_slot[warp];
+
+	const uint32_t voxNum = lane + (request & 15u) * 32u;
+	const int local = nth_voxel(slot.mask, slot.prefix, slot.numVoxels, voxNum);
+	if(local < 0)
+	{
+		out[lane] = 0; out[32 + lane] = 0; out[64 + lane] = 0;
+		return;
+	}
+
+	LightCtx cx;
+	ray_state_reset(cx.st);
+	cx.lc = DnbCounters{0, 0, 0, 0, 0, 0, 0};
+	cx.firstSample = false;
+	cx.sourceVisible = (__ldg(S.visible + (mapIndex >> 5)) >> (mapIndex & 31u)) & 1u;
+
+	const i3 chunkPos = {local & 7, (local >> 3) & 7, local >> 6};
+	const i3 mapPos = {slot.pos[0], slot.pos[1], slot.pos[2]};
+
+	const uint4 rec = __ldg(S.records + (slot.voxelBase + voxNum));
+	const f3 normal = vox_normal(rec);
+	const f3 albedo = vox_albedo(rec);
+	const DnbMaterial material = load_material(S, vox_material(rec));
+
+	const uint32_t ns = slot.numSamples; /* pre-dispatch value for every group of the chunk (N2) */
+	const float indirectSamples = (float)(ns < c_light.maxDiffuseSamples ? ns : c_light.maxDiffuseSamples);
+	if(indirectSamples == 0.0f)
+		cx.firstSample = true;
+
+	/* LI:231-232 */
+	f3 rayPos = (tof3(chunkPos) * 0.125f + tof3(mapPos)) + 0.0625f;
+	rayPos = rayPos + normal * (0.0625f - DNB_EPSILON);
+
+	f3 specLight = splat3(0.0f);
+	f3 diffuseLight = splat3(0.0f);
+
+	/* LI:239-251 */
+	const f3 viewDir = rayPos - ld3(c_light.camPos);
+	if(material.specular > 0.0f && dot3(viewDir, normal) < 0.0f && material.reflectType <= 1u)
+	{
+		const f3 reflected = reflect3(normalize3(viewDir), normal);
+		for(int i = 0; i < 15; i++)
+		{
+			f3 specDir = normalize3(reflected * (float)material.shininess + ld3(c_spherePoints[i])) + DNB_EPSILON;
+			specular_ray<COUNT>(S, cx, rayPos, specDir, albedo, material.reflectType, specLight);
+		}
+		specLight = div3(specLight, 15.0f);
+	}
+
+	/* LI:254-264 */
+	if(material.specular < 1.0f)
+	{
+		const f3 ambient = ld3(S.ambient);
+		for(uint32_t i = 0; i < c_light.numDiffuseSamples; i++)
+		{
+			diffuseLight = diffuseLight + ambient;
+			diffuse_ray<COUNT>(S, cx, normal + DNB_EPSILON, rayPos, rec, i, diffuseLight);
+			shadow_ray<COUNT>(S, cx, rayPos, i, diffuseLight);
+		}
+		const float denom = indirectSamples + (float)c_light.numDiffuseSamples;
+		diffuseLight = div3(vox_diffuse(rec) * indirectSamples + diffuseLight, denom);
+	}
+
+	specLight = clamp01(specLight);
+	diffuseLight = clamp01(diffuseLight);
+
+	/* LI:271-278; round() = nearest even (N6) */
+	const uint32_t wx = (uint32_t)rintf(diffuseLight.x * 65535.0f);
+	const uint32_t wy = (uint32_t)rintf(diffuseLight.y * 65535.0f);
+	const uint32_t wz = (uint32_t)rintf(diffuseLight.z * 65535.0f);
+
+	out[lane]      = encode_rgba((uint32_t)rintf(albedo.x * 255.0f), (uint32_t)rintf(albedo.y * 255.0f), (uint32_t)rintf(albedo.z * 255.0f), (uint32_t)rintf(specLight.x * 255.0f));
+	out[32 + lane] = encode_rgba((uint32_t)rintf(specLight.y * 255.0f), (uint32_t)rintf(specLight.z * 255.0f), (wx >> 8) & 0xFFu, wx & 0xFFu);
+	out[64 + lane] = encode_rgba((wy >> 8) & 0xFFu, wy & 0xFFu, (wz >> 8) & 0xFFu, wz & 0xFFu);
+
+	if(COUNT)
+	{
+		atomicAdd(&S.counters->rays, cx.lc.rays);
+		atomicAdd(&S.counters->tiles, cx.lc.tiles);
+		atomicAdd(&S.counters->chunks, cx.lc.chunks);
+		atomicAdd(&S.counters->voxelSteps, cx.lc.voxelSteps);
+		atomicAdd(&S.counters->records, cx.lc.records);
+		atomicAdd(&S.counters->voxelsLit, 1ull);
+	}
+}
+
+/* phase 2: one warp per request */
+__global__ void __launch_bounds__(256) dn_commit_kernel(const uint32_t* __restrict__ tileSlot, DnbSlot* __restrict__ slots, uint4* __restrict__ records, uint32_t* __restrict__ visible,
+                                                        const uint32_t* __restrict__ requests, uint32_t numRequests, const uint32_t* __restrict__ staging)
+{
+	const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if(r >= numRequests)
+		return;
+	const uint32_t request = __ldg(requests + r);
+	const uint32_t mapIndex = request >> 4, group = request & 15u;
+	const uint32_t slotId = __ldg(tileSlot + mapIndex) - 1u;
+	if(slotId == 0xFFFFFFFFu)
+		return;
+
+	DnbSlot* slot = slots + slotId;
+	const uint32_t numVoxels = slot->numVoxels, base = slot->voxelBase;
+	const uint32_t voxNum = lane + group * 32u;
+	if(voxNum < numVoxels)
+	{
+		const uint32_t* in = staging + (size_t)r * 96u;
+		uint4 rec;
+		rec.x = records[base + voxNum].x;
+		rec.y = __ldg(in + lane);
+		rec.z = __ldg(in + 32 + lane);
+		rec.w = __ldg(in + 64 + lane);
+		records[base + voxNum] = rec;
+	}
+	if(lane == 0 && group * 32u < numVoxels)
+	{
+		atomicAnd(visible + (mapIndex >> 5), ~(1u << (mapIndex & 31u)));
+		if(group == 0)
+			slot->numSamples = slot->numSamples + 1u;
+	}
+}
+
+__global__ void dn_merge_visible_kernel(uint32_t* __restrict__ visible, uint32_t* __restrict__ propagate, uint32_t numWords)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= numWords)
+		return;
+	const uint32_t p = propagate[i];
+	if(p)
+	{
+		visible[i] |= p;
+		propagate[i] = 0;
+	}
+}
+
+extern "C" cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream)
+{
+	return cudaMemcpyToSymbolAsync(c_light, params, sizeof(DnbLightParams), 0, cudaMemcpyHostToDevice, stream);
+}
+
+extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* staging, cudaStream_t stream)
+{
+	if(numRequests == 0)
+		return cudaSuccess;
+	const unsigned grid = (numRequests + 3) / 4;
+	if(scene->counters)
+		dn_light_kernel<true><<<grid, 128, 0, stream>>>(*scene, requests, firstRequest, numRequests, staging);
+	else
+		dn_light_kernel<false><<<grid, 128, 0, stream>>>(*scene, requests, firstRequest, numRequests, staging);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging, cudaStream_t stream)
+{
+	if(numRequests > 0)
+	{
+		dn_commit_kernel<<<(numRequests + 7) / 8, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging);
+		cudaError_t e = cudaGetLastError();
+		if(e != cudaSuccess)
+			return e;
+	}
+	const uint32_t words = (scene->numTiles + 31) / 32;
+	dn_merge_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(scene->visible, scene->propagate, words);
+	return cudaGetLastError();
+}

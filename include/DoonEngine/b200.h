@@ -1,0 +1,96 @@
+/* DoonEngine/b200.h -- additive entry points of libdoon_b200.so.  Nothing here changes the meaning of a
+ * reference symbol (DoonEngine/voxel.h); these exist because the CUDA back end has no OpenGL objects to hand out,
+ * and because tests, benchmarks and the multi-GPU host need to see device state.
+ *
+ * Reference interface each group stands in for:
+ *   framebuffers      the GL_RGBA32F texture the application creates and passes to DN_draw as `outputTexture`
+ *                     (reference main.c:304-357; glBindImageTexture at voxel.c:820)
+ *   device state      glMapBuffer / glGetBufferSubData on vol->gl{Map,Chunk,Voxel}BufferID (voxel.c:731)
+ *   lighting phases   the single glDispatchCompute at voxel.c:950, split into compute + commit so the lit records
+ *                     can be exchanged between GPUs in between
+ */
+#ifndef DN_B200_H
+#define DN_B200_H
+
+#include "voxel.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device selection (call before DN_init; default = device 0 or $DN_B200_DEVICE) ---- */
+int  DN_b200_device_count(void);
+bool DN_b200_set_device(int ordinal);
+/* run all kernels of this library on a caller-owned CUDA stream (cudaStream_t), NULL = the library's own */
+void DN_b200_set_stream(void* cudaStream);
+/* blocks until everything queued by this library has finished; false + message on a CUDA error */
+bool DN_b200_synchronize(void);
+
+/* ---- framebuffers: linear RGBA32F, row 0 = screen y -1, usable as DN_draw's outputTexture ---- */
+GLuint DN_b200_create_framebuffer(int width, int height);
+void   DN_b200_delete_framebuffer(GLuint fb);
+bool   DN_b200_framebuffer_size(GLuint fb, int* width, int* height);
+void*  DN_b200_framebuffer_device_ptr(GLuint fb);                     /* float4[width*height] in device memory */
+bool   DN_b200_read_framebuffer(GLuint fb, float* dst, size_t bytes); /* synchronous device -> host copy */
+bool   DN_b200_clear_framebuffer(GLuint fb, float value);
+
+/* per-pixel first-hit capture for parity tests: status 0 box miss / 1 no hit / 2 hit, tile, voxel, record-in-chunk */
+typedef struct DNb200hit { int32_t status; uint32_t mapIndex, localIndex, recordIndex; } DNb200hit;
+bool DN_b200_capture_hits(GLuint fb, bool enable);
+bool DN_b200_read_hits(GLuint fb, DNb200hit* dst, size_t count);
+
+/* ---- request list ---- */
+/* copies the device-built request list into vol->lightingRequests (growing it like voxel.c:1474-1484); returns the count */
+size_t DN_b200_fetch_lighting_requests(DNvolume* vol);
+
+/* ---- device state download (synchronous).  Returns bytes written, 0 on error / too small a buffer ---- */
+typedef enum DNb200array
+{
+	DN_B200_TILE_SLOTS = 0, /* uint32 per tile: 0 = not resident, else chunk slot + 1 */
+	DN_B200_VISIBLE    = 1, /* uint32 words, 1 bit per tile, flat index order */
+	DN_B200_SLOTS      = 2, /* 128-byte chunk slots (csrc/layout.h DnbSlot), slot-cap entries */
+	DN_B200_RECORDS    = 3, /* 16-byte voxel records, record-cap entries */
+	DN_B200_REQUESTS   = 4, /* uint32 request words of the last reading sync */
+	DN_B200_STAGING    = 5  /* 96 uint32 per request: the lit words of the last lighting compute phase */
+} DNb200array;
+size_t DN_b200_array_bytes(DNvolume* vol, DNb200array which);
+size_t DN_b200_download(DNvolume* vol, DNb200array which, void* dst, size_t dstBytes);
+void*  DN_b200_array_device_ptr(DNvolume* vol, DNb200array which);
+
+/* ---- instrumentation ---- */
+typedef struct DNb200counters { uint64_t rays, tiles, chunks, voxelSteps, records, voxelsLit, pixels; } DNb200counters;
+/* when enabled the kernels count traversal work (slower); counters accumulate until read with reset */
+bool DN_b200_enable_counters(DNvolume* vol, bool enable);
+bool DN_b200_read_counters(DNvolume* vol, DNb200counters* out, bool reset);
+
+typedef struct DNb200stats
+{
+	uint64_t chunksUploaded, chunksRemoved, bytesUploaded; /* since creation */
+	uint64_t residentChunks, residentRecords;              /* now */
+	uint64_t slotCap, recordCap;
+	float    lastDrawMs, lastCompactMs, lastUploadMs, lastLightMs, lastCommitMs; /* device time of the last call of each kind, when timing is on */
+} DNb200stats;
+void DN_b200_get_stats(DNvolume* vol, DNb200stats* out);
+void DN_b200_enable_timing(bool enable); /* record CUDA events around each kernel group (adds a sync when read) */
+
+/* tiles whose host-side state was changed WITHOUT going through a DN_* call (e.g. writing vol->chunks[i].voxels
+ * directly and setting .updated) must be announced, because DN_sync_gpu does not scan the whole map */
+void DN_b200_touch_tile(DNvolume* vol, DNivec3 mapPos);
+void DN_b200_rescan(DNvolume* vol); /* marks every tile touched: the next writing sync reconciles the whole map */
+
+/* ---- multi-GPU: one process per GPU, the same volume replicated in each ---- */
+/* this process lights requests [rank*ceil(R/world), ...) and draws the rank-th band of 16-pixel rows */
+bool DN_b200_set_shard(DNvolume* vol, int rank, int worldSize);
+/* DN_update_lighting == light_compute + light_commit.  Between the two, a sharded host all-gathers the staging
+ * array (DN_B200_STAGING; each rank's slice is DN_b200_staging_slice_bytes() long at rank*that offset). */
+bool   DN_b200_light_compute(DNvolume* vol, int numDiffuseSamples, int maxDiffuseSamples, float time);
+bool   DN_b200_light_commit(DNvolume* vol);
+size_t DN_b200_staging_slice_bytes(DNvolume* vol);
+/* visible[] |= other[] for a bitmap gathered from another rank (device pointer, same length) */
+bool   DN_b200_or_visible(DNvolume* vol, const void* deviceBitmap);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,227 @@
+"""Parity of the CUDA path (libdoon_b200.so through its C ABI) against the oracle and the committed golden fixtures.
+
+Bit-exact: chunk masks / record bytes after upload, first-hit (status, tile, voxel, record-in-chunk) of every pixel,
+visible bits, lighting-request lists (content and order), sample counts.
+Within tolerance: lit voxel records (conftest.LIGHT_TOL) and pixels (conftest.PIXEL_TOL); in practice the lighting
+words come out bit-identical because the kernels use only IEEE +,-,*,/,sqrt,floor with FMA contraction off and the
+host supplies the random table; pixels differ by the ulps of CUDA powf vs libm powf."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (DEMO, GOLDEN, assert_hits_equal, assert_images_close, assert_records_close, frame_time,
+                      records_by_tile)
+
+pytestmark = pytest.mark.gpu
+
+W, H, FRAMES = 320, 192, 4
+
+
+def _compare_state(cuda, ref_state, what, exact_light=False):
+    st = records_by_tile(cuda)
+    for k in ("tiles", "counts", "masks", "partial", "pos", "samples", "visible"):
+        assert np.array_equal(st[k], ref_state[k]), "%s: %s differs" % (what, k)
+    info = assert_records_close(st["records"], ref_state["records"], what)
+    if exact_light:
+        assert info["exact"], "%s: lighting words not bit-identical (%s)" % (what, info)
+    return info
+
+
+def _protocol(cuda, oracle, frames=FRAMES, w=W, h=H, split=1, num_diffuse=1):
+    """drives both engines through draw -> sync -> light and compares after every step."""
+    cuda.sync(1, 1)
+    oracle.sync(1, 1)
+    _compare_state(cuda, records_by_tile(oracle), "after upload")
+    worst = 0.0
+    for k in range(frames):
+        gi, gh = cuda.draw(w, h, want_hits=True)
+        oi, oh = oracle.draw(w, h, want_hits=True)
+        assert_hits_equal(gh, oh, "frame %d" % k)
+        hit = oh["status"] == 2
+        # record index inside the chunk: the oracle reports it relative to the whole pool
+        worst = max(worst, assert_images_close(gi, oi, "frame %d" % k))
+        cuda.sync(2, split)
+        oracle.sync(2, split)
+        assert cuda.num_requests() == len(oracle.requests())
+        assert np.array_equal(cuda.requests(), oracle.requests()), "frame %d: request lists differ" % k
+        cuda.update_lighting(num_diffuse, 1000, frame_time(k))
+        oracle.update_lighting(num_diffuse, 1000, frame_time(k))
+        _compare_state(cuda, records_by_tile(oracle), "frame %d" % k)
+    return worst
+
+
+def test_demo_map_against_golden(dn):
+    """the bundled demo map: every material kind the reference ships, compared with the committed reference run."""
+    g = np.load(os.path.join(GOLDEN, "demo_frames.npz"))
+    e = dn.Engine(voxvol=DEMO, min_chunks=256)
+    e.sync(1, 1)
+    st = records_by_tile(e)
+    assert np.array_equal(st["tiles"], g["tiles"]) and np.array_equal(st["counts"], g["counts"])
+    assert np.array_equal(st["masks"], g["masks"]) and np.array_equal(st["records"], g["records_uploaded"])
+    for k in range(FRAMES):
+        img, hits = e.draw(W, H, want_hits=True)
+        if k == 0:
+            assert np.array_equal(hits["status"], g["hit_status"])
+            hit = hits["status"] == 2
+            assert np.array_equal(hits["mapIndex"][hit], g["hit_tile"][hit])
+            assert np.array_equal(hits["localIndex"][hit], g["hit_voxel"][hit])
+            assert_images_close(img, g["image0"], "frame 0")
+        e.sync(2, 1)
+        assert np.array_equal(e.requests(), g["requests%d" % k])
+        e.update_lighting(1, 1000, frame_time(k))
+        if k in (0, FRAMES - 1):
+            st = records_by_tile(e)
+            assert_records_close(st["records"], g["records%d" % k], "frame %d" % k)
+            assert np.array_equal(st["samples"], g["samples%d" % k])
+            assert np.array_equal(st["visible"], g["visible%d" % k])
+    assert_images_close(e.draw(W, H), g["image_final"], "final image")
+    e.close()
+
+
+def test_demo_map_against_oracle_720p(dn, oracle_mod):
+    """config 1 of BASELINE.json: demo map, 1280x720, draw + lighting update."""
+    e = dn.Engine(voxvol=DEMO, min_chunks=256)
+    o = oracle_mod.OracleEngine(voxvol=DEMO, min_chunks=256)
+    _protocol(e, o, frames=2, w=1280, h=720)
+    e.close()
+    o.close()
+
+
+def test_mixed_materials_scene(dn, oracle_mod):
+    from doonengine_b200 import scenes
+    e = dn.Engine(map_size=(6, 4, 6), min_chunks=64)
+    o = oracle_mod.OracleEngine(map_size=(6, 4, 6), min_chunks=64)
+    for eng in (e, o):
+        scenes.build(eng, scenes.mixed_materials(), **scenes.mixed_camera())
+    _protocol(e, o, frames=6)
+    e.close()
+    o.close()
+
+
+def test_terrain_accumulation(dn, oracle_mod):
+    """config 2 in miniature: procedural terrain, 16 accumulated frames, two diffuse samples per dispatch."""
+    from doonengine_b200 import scenes
+    tiles = (12, 8, 12)
+    e = dn.Engine(map_size=tiles, min_chunks=64)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    for eng in (e, o):
+        scenes.build(eng, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+    _protocol(e, o, frames=16, w=256, h=144, num_diffuse=2)
+    e.close()
+    o.close()
+
+
+def test_lighting_split_and_edits(dn, oracle_mod):
+    """lightingSplit > 1 and chunk edits between frames: request selection (mapIndex % split == frameNum, edited chunks
+    always), re-upload with lighting reset, chunk removal when the last voxel goes."""
+    from doonengine_b200 import scenes
+    tiles = (6, 4, 6)
+    e = dn.Engine(map_size=tiles, min_chunks=8)      # small pools: exercises the automatic growth
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=8)
+    for eng in (e, o):
+        scenes.build(eng, scenes.mixed_materials(tiles), **scenes.mixed_camera(tiles))
+        eng.sync(1, 1)
+    rng = np.random.default_rng(11)
+    for k in range(8):
+        gi, gh = e.draw(W, H, want_hits=True)
+        oi, oh = o.draw(W, H, want_hits=True)
+        assert_hits_equal(gh, oh, "frame %d" % k)
+        assert_images_close(gi, oi, "frame %d" % k)
+        # edits: 40 random voxel sets/removals, plus the removal of one whole chunk every other frame
+        for _ in range(40):
+            p = rng.integers(0, [tiles[0] * 8, 16, tiles[2] * 8])
+            mp, cp = tuple(int(x) // 8 for x in p), tuple(int(x) % 8 for x in p)
+            if rng.random() < 0.5:
+                nw, aw = 0xFF000000 | int(rng.integers(0, 1 << 24)), 0
+            else:
+                nw, aw = e.compress_voxel(int(rng.integers(0, 5)), (0.0, 1.0, 0.0), tuple(int(x) for x in rng.integers(32, 240, 3)))
+            for eng in (e, o):
+                eng.set_voxel(mp, cp, nw, aw)
+        if k % 2 == 1:
+            mp = (int(rng.integers(0, tiles[0])), 0, int(rng.integers(0, tiles[2])))
+            empty = np.full((8, 8, 8, 2), 0xFFFFFFFF, np.uint32)
+            for eng in (e, o):
+                for x in range(8):
+                    for y in range(8):
+                        for z in range(8):
+                            eng.set_voxel(mp, (x, y, z), 0xFFFFFFFF, 0)
+        for eng in (e, o):
+            eng.sync(2, 3)
+        assert np.array_equal(e.requests(), o.requests()), "frame %d: request lists differ" % k
+        for eng in (e, o):
+            eng.update_lighting(1, 1000, frame_time(k))
+        _compare_state(e, records_by_tile(o), "frame %d" % k)
+    e.close()
+    o.close()
+
+
+def test_view_modes(dn, oracle_mod):
+    e = dn.Engine(voxvol=DEMO, min_chunks=256)
+    o = oracle_mod.OracleEngine(voxvol=DEMO, min_chunks=256)
+    for eng in (e, o):
+        eng.sync(1, 1)
+        eng.draw(W, H)
+        eng.sync(2, 1)
+        eng.update_lighting(1, 1000, 1.0)
+    for mode in range(6):
+        e.set_params(camViewMode=mode)
+        o.set_params(camViewMode=mode)
+        assert_images_close(e.draw(W, H), o.draw(W, H), "view mode %d" % mode)
+    e.close()
+    o.close()
+
+
+def test_camera_inside_and_outside(dn, oracle_mod):
+    """rays that start inside the map, outside it, and that miss the box entirely (alpha = -1, oracle.h N7)."""
+    for cam in (dict(camPos=(5.0, 1.5, 5.0), camOrient=(10.0, 200.0, 0.0)), dict(camPos=(-8.0, 9.0, -8.0), camOrient=(35.0, 45.0, 0.0)),
+                dict(camPos=(5.0, 8.0, 5.0), camOrient=(-60.0, 10.0, 0.0)), dict(camPos=(4.3, 1.2, 20.0), camOrient=(0.0, 180.0, 5.0))):
+        e = dn.Engine(voxvol=DEMO, min_chunks=256)
+        o = oracle_mod.OracleEngine(voxvol=DEMO, min_chunks=256)
+        for eng in (e, o):
+            eng.set_params(**cam)
+        _protocol(e, o, frames=1, w=208, h=128)
+        e.close()
+        o.close()
+
+
+def test_counters_match_oracle(dn, oracle_mod):
+    """the traversal counters behind the ALGORITHMIC byte count are identical to the oracle's."""
+    e = dn.Engine(voxvol=DEMO, min_chunks=256)
+    o = oracle_mod.OracleEngine(voxvol=DEMO, min_chunks=256)
+    assert e.enable_counters(True)
+    for eng in (e, o):
+        eng.sync(1, 1)
+    e.counters(reset=True)
+    o.reset_counters()
+    e.draw(W, H)
+    o.draw(W, H)
+    gd, od = e.counters(reset=True), o.counters()["draw"]
+    for k in ("rays", "tiles", "chunks", "voxelSteps", "records", "pixels"):
+        assert gd[k] == od[k], (k, gd, od)
+    for eng in (e, o):
+        eng.sync(2, 1)
+        eng.update_lighting(1, 1000, 1.0)
+    gl, ol = e.counters(reset=True), o.counters()["light"]
+    for k in ("rays", "tiles", "chunks", "voxelSteps", "records", "voxelsLit"):
+        assert gl[k] == ol[k], (k, gl, ol)
+    e.close()
+    o.close()
+
+
+def test_empty_map_and_odd_sizes(dn, oracle_mod):
+    """empty volume (no chunks, no requests) and an image whose size is not a multiple of 16 (voxel.c:879 truncation)."""
+    e = dn.Engine(map_size=(3, 2, 5), min_chunks=4)
+    o = oracle_mod.OracleEngine(map_size=(3, 2, 5), min_chunks=4)
+    for eng in (e, o):
+        eng.set_params(camPos=(-1.0, 1.0, -1.0), camOrient=(10.0, 45.0, 0.0))
+        eng.sync(2, 1)
+    assert e.num_requests() == 0
+    gi = e.draw(200, 120)
+    oi = o.draw(200, 120)
+    assert_images_close(gi, oi, "empty map")
+    assert (gi[112:] == 0).all() and (gi[:, 192:] == 0).all()
+    e.update_lighting(1, 1000, 1.0)
+    e.synchronize()
+    e.close()
+    o.close()
