@@ -77,7 +77,7 @@ class DNb200counters(C.Structure):
 class DNb200stats(C.Structure):
     _fields_ = [("chunksUploaded", C.c_uint64), ("chunksRemoved", C.c_uint64), ("bytesUploaded", C.c_uint64),
                 ("residentChunks", C.c_uint64), ("residentRecords", C.c_uint64),
-                ("slotCap", C.c_uint64), ("recordCap", C.c_uint64),
+                ("slotCap", C.c_uint64), ("recordCap", C.c_uint64), ("voxelsLit", C.c_uint64),
                 ("lastDrawMs", C.c_float), ("lastCompactMs", C.c_float), ("lastUploadMs", C.c_float),
                 ("lastLightMs", C.c_float), ("lastCommitMs", C.c_float)]
 

@@ -97,6 +97,7 @@ bool device_create(VolumeImpl* v)
 	ok = ok && device_reserve(v->blockCounts, cb ? cb : 1, false, true, "compaction counts");
 	ok = ok && device_reserve(v->blockOffsets, cb ? cb : 1, false, true, "compaction offsets");
 	ok = ok && device_reserve(v->scalars, 16, false, true, "scalars");
+	ok = ok && device_reserve(v->litCounter, 1, false, true, "lit counter");
 	if(ok && !v->pinnedScalars)
 		ok = cuda_ok(cudaMallocHost((void**)&v->pinnedScalars, 16 * sizeof(uint32_t)), "pinned scalars");
 	if(!ok)
@@ -120,7 +121,7 @@ void device_destroy(VolumeImpl* v)
 	}
 	device_free(v->tileSlot); device_free(v->occ64); device_free(v->visible); device_free(v->propagate); device_free(v->forced);
 	device_free(v->slots); device_free(v->records); device_free(v->materials); device_free(v->requests); device_free(v->staging);
-	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->blob);
+	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->blob); device_free(v->litCounter);
 	if(v->pinnedBlob) cudaFreeHost(v->pinnedBlob);
 	if(v->pinnedScalars) cudaFreeHost(v->pinnedScalars);
 	if(v->counters) cudaFree(v->counters);
@@ -951,7 +952,7 @@ static bool light_commit(VolumeImpl* v)
 	DnbScene scene;
 	fill_scene(v, &scene);
 	ScopedTimer timer(&v->stats.lastCommitMs, s);
-	return cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, (uint32_t)v->stagedRequests, v->staging.ptr, s), "commit kernel");
+	return cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, (uint32_t)v->stagedRequests, v->staging.ptr, v->litCounter.ptr, s), "commit kernel");
 }
 
 extern "C" void DN_update_lighting(DNvolume* vol, int numDiffuseSamples, int maxDiffuseSamples, float time)
@@ -1125,6 +1126,12 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 	VolumeImpl* v = impl_of(vol);
 	v->stats.slotCap = v->slots.cap;
 	v->stats.recordCap = v->records.cap;
+	if(ctx().ready && v->litCounter.ptr && DN_b200_synchronize())
+	{
+		unsigned long long lit = 0;
+		if(cuda_ok(cudaMemcpy(&lit, v->litCounter.ptr, sizeof(lit), cudaMemcpyDeviceToHost), "lit counter read"))
+			v->stats.voxelsLit = lit;
+	}
 	*out = v->stats;
 }
 

@@ -80,6 +80,7 @@ struct VolumeImpl
 	DeviceArray<uint32_t>           staging;   /* 96 words per request */
 	DeviceArray<uint32_t>           blockCounts, blockOffsets, scalars;
 	DeviceArray<uint32_t>           forcedList;
+	DeviceArray<unsigned long long> litCounter; /* voxel lighting updates committed since creation */
 	DeviceArray<unsigned char>      blob;      /* device side of the upload batch */
 	unsigned char* pinnedBlob = nullptr;
 	size_t         pinnedBlobCap = 0;

@@ -22,7 +22,8 @@ cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, 
 
 cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream);
 cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* staging, cudaStream_t stream);
-cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging, cudaStream_t stream);
+cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
+                              unsigned long long* litCounter, cudaStream_t stream);
 
 uint32_t    dnb_compact_num_blocks(uint32_t numTiles);
 cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets, uint32_t* grandTotal,

@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_
 
 /* phase 2: one warp per request */
 __global__ void __launch_bounds__(256) dn_commit_kernel(const uint32_t* __restrict__ tileSlot, DnbSlot* __restrict__ slots, uint4* __restrict__ records, uint32_t* __restrict__ visible,
-                                                        const uint32_t* __restrict__ requests, uint32_t numRequests, const uint32_t* __restrict__ staging)
+                                                        const uint32_t* __restrict__ requests, uint32_t numRequests, const uint32_t* __restrict__ staging,
+                                                        unsigned long long* __restrict__ litCounter)
 {
 	const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
 	if(r >= numRequests)
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(256) dn_commit_kernel(const uint32_t* __restri
 	DnbSlot* slot = slots + slotId;
 	const uint32_t numVoxels = slot->numVoxels, base = slot->voxelBase;
 	const uint32_t voxNum = lane + group * 32u;
+	const uint32_t live = __ballot_sync(0xFFFFFFFFu, voxNum < numVoxels);
 	if(voxNum < numVoxels)
 	{
 		const uint32_t* in = staging + (size_t)r * 96u;
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(256) dn_commit_kernel(const uint32_t* __restri
 		atomicAnd(visible + (mapIndex >> 5), ~(1u << (mapIndex & 31u)));
 		if(group == 0)
 			slot->numSamples = slot->numSamples + 1u;
+		atomicAdd(litCounter, (unsigned long long)__popc(live)); /* the metric's numerator: voxel lighting updates */
 	}
 }
 
@@ -375,11 +378,12 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 	return cudaGetLastError();
 }
 
-extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging, cudaStream_t stream)
+extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
+                                         unsigned long long* litCounter, cudaStream_t stream)
 {
 	if(numRequests > 0)
 	{
-		dn_commit_kernel<<<(numRequests + 7) / 8, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging);
+		dn_commit_kernel<<<(numRequests + 7) / 8, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging, litCounter);
 		cudaError_t e = cudaGetLastError();
 		if(e != cudaSuccess)
 			return e;

@@ -126,30 +126,30 @@ def terrain(tiles=(64, 64, 64), seed=1234, base=None, amp=None):
     for cz in range(tz):
         for cx in range(tx):
             hcol = hi[cx * 8:cx * 8 + 8, cz * 8:cz * 8 + 8]       # [x, z]
-            top = int(hcol.max())
+            layers = min(ty, (int(hcol.max()) + 7) // 8)
             xs = np.arange(cx * 8, cx * 8 + 8, dtype=np.int64)
             zs = np.arange(cz * 8, cz * 8 + 8, dtype=np.int64)
-            for cy in range(min(ty, (top + 7) // 8)):
-                yy = ys[cy * 8:cy * 8 + 8]
-                solid = yy[None, :, None] < hcol[:, None, :]      # [x, y, z]
-                if not solid.any():
-                    continue
-                X, Y, Z = np.meshgrid(xs, yy, zs, indexing="ij")
-                hsh = hash3(X, Y, Z, seed)
-                surface = (Y >= hcol[:, None, :] - 1)
-                emissive = surface & ((hsh % np.uint32(100)) == 0)
-                mat = np.where(emissive, np.uint32(2), np.uint32(0))
-                # height bands: sand / grass / rock / snow, jittered per voxel
-                t = Y.astype(np.float32) / np.float32(ny)
-                jit = ((hsh >> np.uint32(8)) & np.uint32(31)).astype(np.int32) - 16
-                r = np.where(t < 0.22, 194, np.where(t < 0.34, 86, np.where(t < 0.46, 120, 235))) + jit
-                g = np.where(t < 0.22, 178, np.where(t < 0.34, 152, np.where(t < 0.46, 112, 238))) + jit
-                b = np.where(t < 0.22, 128, np.where(t < 0.34, 66, np.where(t < 0.46, 104, 240))) + jit
-                r, g, b = (np.clip(c, 32, 240).astype(np.uint32) for c in (r, g, b))
-                v = np.empty((8, 8, 8, 2), np.uint32)
-                v[..., 0] = np.where(solid, (mat << np.uint32(24)) | nword_xz[cx * 8:cx * 8 + 8, None, cz * 8:cz * 8 + 8], EMPTY)
-                v[..., 1] = albedo_word(r, g, b)
-                yield (cx, cy, cz), v
+            yy = ys[:layers * 8]
+            # the whole column of chunks at once: arrays are [x, y, z] with y spanning `layers` chunks
+            solid = yy[None, :, None] < hcol[:, None, :]
+            X, Y, Z = np.meshgrid(xs, yy, zs, indexing="ij")
+            hsh = hash3(X, Y, Z, seed)
+            surface = (Y >= hcol[:, None, :] - 1)
+            emissive = surface & ((hsh % np.uint32(100)) == 0)
+            mat = np.where(emissive, np.uint32(2), np.uint32(0))
+            # height bands: sand / grass / rock / snow, jittered per voxel
+            t = Y.astype(np.float32) / np.float32(ny)
+            jit = ((hsh >> np.uint32(8)) & np.uint32(31)).astype(np.int32) - 16
+            r = np.where(t < 0.22, 194, np.where(t < 0.34, 86, np.where(t < 0.46, 120, 235))) + jit
+            g = np.where(t < 0.22, 178, np.where(t < 0.34, 152, np.where(t < 0.46, 112, 238))) + jit
+            b = np.where(t < 0.22, 128, np.where(t < 0.34, 66, np.where(t < 0.46, 104, 240))) + jit
+            r, g, b = (np.clip(c, 32, 240).astype(np.uint32) for c in (r, g, b))
+            col = np.empty((8, layers * 8, 8, 2), np.uint32)
+            col[..., 0] = np.where(solid, (mat << np.uint32(24)) | nword_xz[cx * 8:cx * 8 + 8, None, cz * 8:cz * 8 + 8], EMPTY)
+            col[..., 1] = albedo_word(r, g, b)
+            for cy in range(layers):
+                if solid[:, cy * 8:cy * 8 + 8, :].any():
+                    yield (cx, cy, cz), np.ascontiguousarray(col[:, cy * 8:cy * 8 + 8])
 
 
 def terrain_camera(tiles=(64, 64, 64)):

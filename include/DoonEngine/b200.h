@@ -68,9 +68,10 @@ typedef struct DNb200stats
 	uint64_t chunksUploaded, chunksRemoved, bytesUploaded; /* since creation */
 	uint64_t residentChunks, residentRecords;              /* now */
 	uint64_t slotCap, recordCap;
+	uint64_t voxelsLit;                                     /* voxel lighting updates committed since creation */
 	float    lastDrawMs, lastCompactMs, lastUploadMs, lastLightMs, lastCommitMs; /* device time of the last call of each kind, when timing is on */
 } DNb200stats;
-void DN_b200_get_stats(DNvolume* vol, DNb200stats* out);
+void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
 void DN_b200_enable_timing(bool enable); /* record CUDA events around each kernel group (adds a sync when read) */
 
 /* tiles whose host-side state was changed WITHOUT going through a DN_* call (e.g. writing vol->chunks[i].voxels

@@ -437,3 +437,17 @@ void fgl_set_view_projection(DNvolume* vol, float aspect, float nearPlane, float
 	memcpy(view, &v, sizeof(DNmat4));
 	memcpy(projection, &p, sizeof(DNmat4));
 }
+
+/* bulk form of 512 DN_set_compressed_voxel calls (the reference has no bulk entry point); voxels[x][y][z][2] */
+void fgl_set_chunk(DNvolume* vol, int mx, int my, int mz, const uint32_t* voxels)
+{
+	DNivec3 mapPos = {mx, my, mz};
+	for(int x = 0; x < 8; x++)
+		for(int y = 0; y < 8; y++)
+			for(int z = 0; z < 8; z++)
+			{
+				const uint32_t* w = voxels + ((x * 8 + y) * 8 + z) * 2;
+				DNcompressedVoxel v = {w[0], w[1]};
+				DN_set_compressed_voxel(vol, mapPos, (DNivec3){x, y, z}, v);
+			}
+}

@@ -325,6 +325,7 @@ class RefEngine(_EngineBase):
         L.DN_sync_gpu.argtypes = [C.POINTER(DNvolume), C.c_int, C.c_int]
         L.DN_update_lighting.argtypes = [C.POINTER(DNvolume), C.c_int, C.c_int, C.c_float]
         L.DN_set_compressed_voxel.argtypes = [C.POINTER(DNvolume), DNivec3, DNivec3, DNcompressedVoxel]
+        L.fgl_set_chunk.argtypes = [C.POINTER(DNvolume), C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.fgl_draw.argtypes = [C.POINTER(DNvolume), C.c_uint, C.c_void_p, C.c_void_p]
         L.fgl_set_view_projection.argtypes = [C.POINTER(DNvolume), C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.fgl_create_texture.restype = C.c_uint
@@ -381,11 +382,9 @@ class RefEngine(_EngineBase):
                                        self.DNcompressedVoxel(int(normal_word), int(albedo_word)))
 
     def set_chunk(self, map_pos, voxels):
-        a = np.asarray(voxels, dtype=np.uint32)
-        for x in range(8):
-            for y in range(8):
-                for z in range(8):
-                    self.set_voxel(map_pos, (x, y, z), a[x, y, z, 0], a[x, y, z, 1])
+        a = np.ascontiguousarray(voxels, dtype=np.uint32)
+        assert a.shape == (8, 8, 8, 2)
+        self.L.fgl_set_chunk(self.vol, int(map_pos[0]), int(map_pos[1]), int(map_pos[2]), a.ctypes.data)
 
     def sync(self, op=2, split=1):
         """DN_sync_gpu; in resident mode a WRITE sync is followed by the pre-warm of
