@@ -6,9 +6,14 @@
  *              inner loop    SH:328-418  step_chunk: one iteration per voxel of a resident chunk
  * The float arithmetic (sequential sideDist accumulation, entry point min(lastSideDist) -/+ EPSILON, the
  * [EPSILON, 8-EPSILON] clamp) is kept operation for operation because first-hit indices must be bit-exact.
- * What is re-designed is every memory access around it (layout.h): an empty tile costs one bit test in a
- * register-cached 4x4x4 occupancy word, a resident tile one 4-byte slot lookup, a voxel step one bit test
- * in a register-cached mask word of the 128-byte chunk slot, a hit one 16-byte record gather.
+ * What is re-designed is everything around it (layout.h, DESIGN.md "trace"):
+ *   - an empty tile costs one bit test in a register-cached 4x4x4 occupancy word; map bounds are only checked when
+ *     the ray changes block (border blocks are padded with empty tiles), and a fully empty block is crossed by a
+ *     tight loop that runs nothing but the DDA recurrence;
+ *   - a resident tile costs one 4-byte slot lookup, a voxel step one bit test in a register-cached mask word of
+ *     the 128-byte chunk slot, a hit one 16-byte record gather;
+ *   - lastSideDist is carried as its minimum (the only way it is ever used), and the face normal of the last step
+ *     is kept as a 3-bit mask and only materialised where the draw pass needs it (the kernels were ALU-pipe bound).
  *
  * Not implemented (out of scope): raster-depth gating (maxDepth is always < 0, so the test at
  * SH:363 is always true) and demand-stream requests (SH:462-466; the map is resident).
@@ -81,30 +86,49 @@ DNB_FN f3 sky_color(const DnbScene& S, f3 rayDir)
 	return ld3(S.skyBot) * (1.0f - t) + ld3(S.skyTop) * t;
 }
 
-/* SH:300-306 */
-DNB_FN void init_dda(f3 rayDir, f3 invRayDir, f3 rayPos, i3& pos, f3& deltaDist, i3& rayStep, f3& sideDist)
+struct Dda
 {
-	pos = toi3(floor3(rayPos));
-	deltaDist = abs3(invRayDir);
-	f3 sg = mk3(sgn(rayDir.x), sgn(rayDir.y), sgn(rayDir.z));
-	rayStep = toi3(sg);
-	f3 t = sg * (tof3(pos) - rayPos) + sg * 0.5f;
-	sideDist = (t + 0.5f) * deltaDist;
+	i3 pos, step;
+	f3 delta, side;
+};
+
+DNB_FN int isgn(float a) { return (a > 0.0f) ? 1 : ((a < 0.0f) ? -1 : 0); }
+
+/* SH:300-306.  floor(rayPos) is used as a float directly instead of converting the integer cell back
+ * (identical for |rayPos| < 2^24; saves three conversions on the XU pipe per ray segment) */
+DNB_FN void init_dda(f3 rayDir, f3 invRayDir, f3 rayPos, Dda& d)
+{
+	const f3 cell = floor3(rayPos);
+	d.pos = toi3(cell);
+	d.delta = abs3(invRayDir);
+	const f3 sg = mk3(sgn(rayDir.x), sgn(rayDir.y), sgn(rayDir.z));
+	d.step.x = isgn(rayDir.x);
+	d.step.y = isgn(rayDir.y);
+	d.step.z = isgn(rayDir.z);
+	const f3 t = sg * (cell - rayPos) + sg * 0.5f;
+	d.side = (t + 0.5f) * d.delta;
 }
 
-/* SH:309-317; the mask products are selects (identical unless deltaDist is infinite, oracle.h N6) */
-DNB_FN void iterate_dda(f3 deltaDist, i3 rayStep, f3& sideDist, i3& pos, f3& normal)
+/* SH:309-317: every axis whose sideDist is minimal steps (ties step together).  Returns the 3-bit axis mask and
+ * writes min(sideDist) BEFORE the step, which is min(lastSideDist) of the reference (SH:354,360,370,394,443). */
+DNB_FN uint32_t iterate_dda(Dda& d, float& tLast)
 {
-	f3 s = sideDist;
-	bool mx = s.x <= fminf(s.y, s.z);
-	bool my = s.y <= fminf(s.z, s.x);
-	bool mz = s.z <= fminf(s.x, s.y);
-	if(mx) { sideDist.x = s.x + deltaDist.x; pos.x += rayStep.x; }
-	if(my) { sideDist.y = s.y + deltaDist.y; pos.y += rayStep.y; }
-	if(mz) { sideDist.z = s.z + deltaDist.z; pos.z += rayStep.z; }
-	normal.x = (mx ? 1.0f : 0.0f) * (float)(-rayStep.x);
-	normal.y = (my ? 1.0f : 0.0f) * (float)(-rayStep.y);
-	normal.z = (mz ? 1.0f : 0.0f) * (float)(-rayStep.z);
+	const f3 s = d.side;
+	const float myz = fminf(s.y, s.z);
+	const bool mx = s.x <= myz;
+	const bool my = s.y <= fminf(s.z, s.x);
+	const bool mz = s.z <= fminf(s.x, s.y);
+	tLast = fminf(s.x, myz);
+	if(mx) { d.side.x = s.x + d.delta.x; d.pos.x += d.step.x; }
+	if(my) { d.side.y = s.y + d.delta.y; d.pos.y += d.step.y; }
+	if(mz) { d.side.z = s.z + d.delta.z; d.pos.z += d.step.z; }
+	return (mx ? 1u : 0u) | (my ? 2u : 0u) | (mz ? 4u : 0u);
+}
+
+/* normal = vec3(mask) * -rayStep (SH:316), materialised on demand */
+DNB_FN f3 normal_of(uint32_t mask, i3 step)
+{
+	return mk3(((mask & 1u) ? 1.0f : 0.0f) * (float)(-step.x), ((mask & 2u) ? 1.0f : 0.0f) * (float)(-step.y), ((mask & 4u) ? 1.0f : 0.0f) * (float)(-step.z));
 }
 
 DNB_FN bool in_map_bounds(const DnbScene& S, i3 p)
@@ -119,9 +143,10 @@ DNB_FN bool in_chunk_bounds(i3 p)
 
 #define DNB_COUNT(field) do { if(COUNT) lc.field++; } while(0)
 
-/* step_map + step_chunk.  REFRACT: enableRefraction (true in draw, false in lighting, DR:65 / LI:209).
- * invRayDir is by value: a refraction inside a chunk updates the caller's rayDir but only this
- * function's invRayDir, exactly as the inout/in qualifiers at SH:328/421 do. */
+/* step_map + step_chunk.  REFRACT: enableRefraction (true in draw, false in lighting, DR:65 / LI:209); only then is
+ * hitNormal read or written.  invRayDir is by value: a refraction inside a chunk updates the caller's rayDir but only
+ * this function's invRayDir, exactly as the inout/in qualifiers at SH:328/421 do.
+ * COUNT: instrumented build -- exact per-tile bounds checks and counters, no empty-block fast path. */
 template <bool REFRACT, bool COUNT>
 DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayDir, f3 invRayDir, f3& rayPos, bool ignoreFirst, f3& hitNormal, f3& colorAdd, float& colorMult)
 {
@@ -129,17 +154,32 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 	colorMult = 1.0f;
 	DNB_COUNT(rays);
 
-	i3 pos, rayStep;
-	f3 deltaDist, sideDist;
-	f3 lastSideDist = splat3(0.0f);
-	init_dda(rayDir, invRayDir, rayPos, pos, deltaDist, rayStep, sideDist);
+	Dda m;
+	init_dda(rayDir, invRayDir, rayPos, m);
+	float tLast = 0.0f;           /* min(lastSideDist), vec3(0) before the first step (SH:432) */
+
+	/* where the current face normal comes from: 0 = caller's value, 1 = last map-level step, 2 = last voxel-level step */
+	uint32_t nmask = 0, nsrc = 0;
+	Dda c;                        /* voxel-level DDA of the chunk being crossed */
+	c.step.x = c.step.y = c.step.z = 0;
 
 	uint32_t guard = 0;
-	uint32_t occBlock = 0xFFFFFFFFu;
+	i3 blk = {0x40000000, 0x40000000, 0x40000000}; /* base tile of the cached occupancy block (never a real one) */
 	unsigned long long occWord = 0;
 
-	while(in_map_bounds(S, pos))
+	for(;;)
 	{
+		if((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) > 3u)
+		{
+			/* entered another 4x4x4 block: the only place the map bounds are tested */
+			if(!in_map_bounds(S, m.pos))
+				break;
+			blk.x = m.pos.x & ~3; blk.y = m.pos.y & ~3; blk.z = m.pos.z & ~3;
+			occWord = __ldg(S.occ64 + ((uint32_t)(m.pos.x >> 2) + S.blocks[0] * ((uint32_t)(m.pos.y >> 2) + S.blocks[1] * (uint32_t)(m.pos.z >> 2))));
+		}
+		else if(COUNT && !in_map_bounds(S, m.pos))
+			break;
+
 		if(++guard > S.maxMapSteps || st.tripped)
 		{
 			st.tripped = true;
@@ -147,36 +187,40 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 		}
 		DNB_COUNT(tiles);
 
-		uint32_t block = (uint32_t)(pos.x >> 2) + S.blocks[0] * ((uint32_t)(pos.y >> 2) + S.blocks[1] * (uint32_t)(pos.z >> 2));
-		if(block != occBlock)
+		if(!COUNT && occWord == 0ull)
 		{
-			occBlock = block;
-			occWord = __ldg(S.occ64 + block);
+			/* the whole block is empty (or padding outside the map): run the bare DDA recurrence until the ray leaves it */
+			do
+			{
+				nmask = iterate_dda(m, tLast);
+				guard++;
+			} while((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) <= 3u && guard <= S.maxMapSteps);
+			nsrc = 1;
+			ignoreFirst = false;
+			continue;
 		}
-		uint32_t bit = (uint32_t)(pos.x & 3) | ((uint32_t)(pos.y & 3) << 2) | ((uint32_t)(pos.z & 3) << 4);
 
+		const uint32_t bit = (uint32_t)(m.pos.x & 3) | ((uint32_t)(m.pos.y & 3) << 2) | ((uint32_t)(m.pos.z & 3) << 4);
 		if((occWord >> bit) & 1ull)
 		{
-			uint32_t mapIndex = (uint32_t)pos.x + S.mapSize[0] * ((uint32_t)pos.y + S.mapSize[1] * (uint32_t)pos.z);
-			uint32_t slotId = __ldg(S.tileSlot + mapIndex) - 1u;
-			const DnbSlot* slot = S.slots + slotId;
+			const uint32_t mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
+			const DnbSlot* slot = S.slots + (__ldg(S.tileSlot + mapIndex) - 1u);
 			DNB_COUNT(chunks);
 
 			/* SH:443-445: entry point in chunk-local voxel units */
-			f3 entry = rayPos + rayDir * (hmin3(lastSideDist) - DNB_EPSILON);
-			f3 cpos = (entry - tof3(pos)) * 8.0f;
+			const f3 tile = tof3(m.pos);
+			const f3 entry = rayPos + rayDir * (tLast - DNB_EPSILON);
+			f3 cpos = (entry - tile) * 8.0f;
 			cpos = min3v(max3v(cpos, splat3(DNB_EPSILON)), splat3(8.0f - DNB_EPSILON));
 
 			/* ---- step_chunk, SH:328-418 ---- */
 			bool refracted = false;
-			i3 p, cstep;
-			f3 cdelta, cside;
-			f3 clast = splat3(0.0f);
-			init_dda(rayDir, invRayDir, cpos, p, cdelta, cstep, cside);
+			init_dda(rayDir, invRayDir, cpos, c);
+			float ctLast = 0.0f;
 
 			uint32_t cguard = 0;
 			uint32_t wordIdx = 0xFFFFFFFFu, word = 0;
-			while(in_chunk_bounds(p))
+			while(in_chunk_bounds(c.pos))
 			{
 				if(++cguard > DNB_MAX_CHUNK_STEPS)
 				{
@@ -185,7 +229,7 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 				}
 				DNB_COUNT(voxelSteps);
 
-				uint32_t local = (uint32_t)p.x + 8u * ((uint32_t)p.y + 8u * (uint32_t)p.z);
+				const uint32_t local = (uint32_t)c.pos.x + 8u * ((uint32_t)c.pos.y + 8u * (uint32_t)c.pos.z);
 				if((local >> 5) != wordIdx)
 				{
 					wordIdx = local >> 5;
@@ -195,43 +239,52 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 				if(((word >> (local & 31u)) & 1u) && !ignoreFirst)
 				{
 					/* SH:150-169 with per-word prefix counts instead of quarter counts */
-					uint32_t rel = (uint32_t)__ldg(slot->prefix + wordIdx) + __popc(word & ((1u << (local & 31u)) - 1u));
-					uint4 rec = __ldg(S.records + (__ldg(&slot->voxelBase) + rel));
+					const uint32_t rel = (uint32_t)__ldg(slot->prefix + wordIdx) + __popc(word & ((1u << (local & 31u)) - 1u));
+					const uint4 rec = __ldg(S.records + (__ldg(&slot->voxelBase) + rel));
 					DNB_COUNT(records);
 					st.vox = rec;
 
-					DnbMaterial material = load_material(S, rec.x >> 24);
-					uint32_t thisVoxID = (rec.y & 0xFFFFFF00u) | (rec.x >> 24);
+					const DnbMaterial material = load_material(S, rec.x >> 24);
+					const uint32_t thisVoxID = (rec.y & 0xFFFFFF00u) | (rec.x >> 24);
 
 					if(material.opacity == 1.0f)
 					{
-						cpos = cpos + rayDir * (hmin3(clast) + DNB_EPSILON);
-						rayPos = tof3(pos) + cpos * 0.125f; /* SH:451 */
+						cpos = cpos + rayDir * (ctLast + DNB_EPSILON);
+						rayPos = tile + cpos * 0.125f; /* SH:451 */
 						st.hitMapIndex = mapIndex;
 						st.hitLocalIndex = local;
 						st.hitRecord = rel;
+						if(REFRACT && nsrc)
+							hitNormal = normal_of(nmask, nsrc == 2u ? c.step : m.step);
 						return true;
 					}
 					else if(st.lastVoxID != thisVoxID)
 					{
 						/* SH:365-366, maxDepth < 0 */
-						float cm = colorMult * material.opacity;
+						const float cm = colorMult * material.opacity;
 						colorAdd = colorAdd + (vox_albedo(rec) * cm) * ld3(S.sunStrength);
 						colorMult = colorMult * (1.0f - material.opacity);
 
 						if(REFRACT)
 						{
-							float rayDist = hmin3(clast);
+							const float rayDist = ctLast;
 							if(rayDist > 0.0f)
 							{
 								refracted = true;
 								cpos = cpos + rayDir * (rayDist + DNB_EPSILON);
-								f3 vn = vox_normal(rec);
-								f3 n = dot3(vn, rayDir) < 0.0f ? normalize3(vn) : hitNormal;
+								const f3 vn = vox_normal(rec);
+								const f3 faceNormal = nsrc ? normal_of(nmask, nsrc == 2u ? c.step : m.step) : hitNormal;
+								const f3 n = dot3(vn, rayDir) < 0.0f ? normalize3(vn) : faceNormal;
 								rayDir = refract3(rayDir, n, st.lastVoxRefract / material.refractIndex);
 								invRayDir = rcp3(rayDir);
-								init_dda(rayDir, invRayDir, cpos, p, cdelta, cstep, cside);
-								clast = splat3(0.0f);
+								if(nsrc)
+								{
+									/* the pending normal refers to the step vectors about to be replaced */
+									hitNormal = faceNormal;
+									nsrc = 0;
+								}
+								init_dda(rayDir, invRayDir, cpos, c);
+								ctLast = 0.0f;
 							}
 						}
 
@@ -244,40 +297,59 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 					if(REFRACT)
 					{
 						refracted = true;
-						cpos = cpos + rayDir * (hmin3(clast) + DNB_EPSILON);
-						f3 oldDir = rayDir;
-						f3 nn = -vox_normal(st.vox);
-						f3 n = dot3(nn, rayDir) < 0.0f ? normalize3(nn) : hitNormal;
+						cpos = cpos + rayDir * (ctLast + DNB_EPSILON);
+						const f3 oldDir = rayDir;
+						const f3 nn = -vox_normal(st.vox);
+						const f3 faceNormal = nsrc ? normal_of(nmask, nsrc == 2u ? c.step : m.step) : hitNormal;
+						const f3 n = dot3(nn, rayDir) < 0.0f ? normalize3(nn) : faceNormal;
 						rayDir = refract3(rayDir, n, st.lastVoxRefract);
 						if(rayDir.x == 0.0f && rayDir.y == 0.0f && rayDir.z == 0.0f)
 							rayDir = oldDir;
 						invRayDir = rcp3(rayDir);
-						init_dda(rayDir, invRayDir, cpos, p, cdelta, cstep, cside);
-						clast = splat3(0.0f);
+						if(nsrc)
+						{
+							hitNormal = faceNormal;
+							nsrc = 0;
+						}
+						init_dda(rayDir, invRayDir, cpos, c);
+						ctLast = 0.0f;
 					}
 					st.lastVoxID = 255u;
 					st.lastVoxRefract = 1.0f;
 				}
 
-				clast = cside;
-				iterate_dda(cdelta, cstep, cside, p, hitNormal);
+				nmask = iterate_dda(c, ctLast);
+				nsrc = 2;
 				ignoreFirst = false;
 			}
 			/* ---- end step_chunk ---- */
 
 			if(REFRACT && refracted)
 			{
-				rayPos = tof3(pos) + cpos * 0.125f;
-				init_dda(rayDir, invRayDir, rayPos, pos, deltaDist, rayStep, sideDist);
-				lastSideDist = splat3(0.0f);
+				if(nsrc)
+				{
+					hitNormal = normal_of(nmask, nsrc == 2u ? c.step : m.step);
+					nsrc = 0;
+				}
+				rayPos = tile + cpos * 0.125f;
+				init_dda(rayDir, invRayDir, rayPos, m);
+				tLast = 0.0f;
+			}
+			else if(REFRACT && nsrc == 2u)
+			{
+				/* the voxel-level step vector goes out of use: pin the normal it produced */
+				hitNormal = normal_of(nmask, c.step);
+				nsrc = 0;
 			}
 		}
 
-		lastSideDist = sideDist;
-		iterate_dda(deltaDist, rayStep, sideDist, pos, hitNormal);
+		nmask = iterate_dda(m, tLast);
+		nsrc = 1;
 		ignoreFirst = false;
 	}
 
+	if(REFRACT && nsrc)
+		hitNormal = normal_of(nmask, nsrc == 2u ? c.step : m.step);
 	return false;
 }
 
