@@ -139,6 +139,11 @@ void fill_scene(VolumeImpl* v, DnbScene* s)
 	s->blocks[0] = v->blocks[0]; s->blocks[1] = v->blocks[1]; s->blocks[2] = v->blocks[2];
 	s->numTiles = (uint32_t)num_tiles(vol);
 	s->maxMapSteps = 4u * (vol->mapSize.x + vol->mapSize.y + vol->mapSize.z) + 256u;
+	for(int a = 0; a < 3; a++)
+	{
+		s->occMin[a] = v->occMin[a];
+		s->occMax[a] = v->occMax[a];
+	}
 	s->occ64 = v->occ64.ptr;
 	s->tileSlot = v->tileSlot.ptr;
 	s->slots = v->slots.ptr;
@@ -400,6 +405,11 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 			v->stats.residentChunks++;
 		}
 		hHeaders[i].voxelBase = acquire_node(v, slotPlus1 - 1, n);
+		for(int a = 0; a < 3; a++)
+		{
+			v->occMin[a] = std::min(v->occMin[a], hHeaders[i].pos[a]);
+			v->occMax[a] = std::max(v->occMax[a], hHeaders[i].pos[a]);
+		}
 		hItems[i].slotPlus1 = slotPlus1;
 		vol->chunks[items[i].chunkIndex].numVoxelsGpu = n; /* voxel.c:1523 */
 		v->stats.chunksUploaded++;

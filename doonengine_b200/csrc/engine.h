@@ -70,6 +70,7 @@ struct VolumeImpl
 
 	/* ---- device ---- */
 	uint32_t blocks[3];
+	int32_t  occMin[3] = {0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF}, occMax[3] = {-0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF};
 	DeviceArray<uint32_t>           tileSlot;
 	DeviceArray<unsigned long long> occ64;
 	DeviceArray<uint32_t>           visible, propagate, forced;

@@ -82,6 +82,7 @@ typedef struct DnbScene
 	uint32_t blocks[3];          /* ceil(mapSize / 4) */
 	uint32_t numTiles;
 	uint32_t maxMapSteps;        /* 4*(sx+sy+sz)+256 */
+	int32_t  occMin[3], occMax[3]; /* inclusive tile bounding box of everything ever resident (conservative) */
 	const unsigned long long* occ64;
 	const uint32_t*    tileSlot;
 	const DnbSlot*     slots;

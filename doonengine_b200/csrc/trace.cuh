@@ -169,39 +169,63 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 
 	for(;;)
 	{
-		if((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) > 3u)
+		/* ---- phase A: advance tile by tile to the next resident chunk.  Kept as its own loop ("while-while"
+		 * traversal) so that the lanes of a warp search together and then cross their chunks together, instead of
+		 * every lane that reaches a chunk stalling the lanes that are still stepping over empty tiles. ---- */
+		bool found = false;
+		for(;;)
 		{
-			/* entered another 4x4x4 block: the only place the map bounds are tested */
-			if(!in_map_bounds(S, m.pos))
-				break;
-			blk.x = m.pos.x & ~3; blk.y = m.pos.y & ~3; blk.z = m.pos.z & ~3;
-			occWord = __ldg(S.occ64 + ((uint32_t)(m.pos.x >> 2) + S.blocks[0] * ((uint32_t)(m.pos.y >> 2) + S.blocks[1] * (uint32_t)(m.pos.z >> 2))));
-		}
-		else if(COUNT && !in_map_bounds(S, m.pos))
-			break;
-
-		if(++guard > S.maxMapSteps || st.tripped)
-		{
-			st.tripped = true;
-			return false;
-		}
-		DNB_COUNT(tiles);
-
-		if(!COUNT && occWord == 0ull)
-		{
-			/* the whole block is empty (or padding outside the map): run the bare DDA recurrence until the ray leaves it */
-			do
+			if((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) > 3u)
 			{
-				nmask = iterate_dda(m, tLast);
-				guard++;
-			} while((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) <= 3u && guard <= S.maxMapSteps);
+				/* entered another 4x4x4 block: the only place the map bounds are tested */
+				if(!in_map_bounds(S, m.pos))
+					break;
+				/* exact early-out: past the bounding box of everything resident and moving away from it, the ray can
+				 * only miss, and nothing of its DDA state is used after a miss */
+				if(!COUNT && ((m.pos.x > S.occMax[0] && m.step.x >= 0) || (m.pos.x < S.occMin[0] && m.step.x <= 0) ||
+				              (m.pos.y > S.occMax[1] && m.step.y >= 0) || (m.pos.y < S.occMin[1] && m.step.y <= 0) ||
+				              (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0)))
+					break;
+				blk.x = m.pos.x & ~3; blk.y = m.pos.y & ~3; blk.z = m.pos.z & ~3;
+				occWord = __ldg(S.occ64 + ((uint32_t)(m.pos.x >> 2) + S.blocks[0] * ((uint32_t)(m.pos.y >> 2) + S.blocks[1] * (uint32_t)(m.pos.z >> 2))));
+			}
+			else if(COUNT && !in_map_bounds(S, m.pos))
+				break;
+
+			if(++guard > S.maxMapSteps || st.tripped)
+			{
+				st.tripped = true;
+				break;
+			}
+			DNB_COUNT(tiles);
+
+			if(!COUNT && occWord == 0ull)
+			{
+				/* the whole block is empty (or padding outside the map): run the bare DDA recurrence until the ray leaves it */
+				do
+				{
+					nmask = iterate_dda(m, tLast);
+					guard++;
+				} while((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) <= 3u && guard <= S.maxMapSteps);
+				nsrc = 1;
+				ignoreFirst = false;
+				continue;
+			}
+
+			const uint32_t bit = (uint32_t)(m.pos.x & 3) | ((uint32_t)(m.pos.y & 3) << 2) | ((uint32_t)(m.pos.z & 3) << 4);
+			if((occWord >> bit) & 1ull)
+			{
+				found = true;
+				break;
+			}
+			nmask = iterate_dda(m, tLast);
 			nsrc = 1;
 			ignoreFirst = false;
-			continue;
 		}
+		if(!found)
+			break;
 
-		const uint32_t bit = (uint32_t)(m.pos.x & 3) | ((uint32_t)(m.pos.y & 3) << 2) | ((uint32_t)(m.pos.z & 3) << 4);
-		if((occWord >> bit) & 1ull)
+		/* ---- phase B: cross the resident chunk voxel by voxel ---- */
 		{
 			const uint32_t mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
 			const DnbSlot* slot = S.slots + (__ldg(S.tileSlot + mapIndex) - 1u);

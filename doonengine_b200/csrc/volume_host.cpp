@@ -539,6 +539,11 @@ extern "C" bool DN_set_map_size(DNvolume* vol, DNuvec3 size)
 	for(int c = 0; c < NUM_NODE_CLASSES; c++)
 		v->freeNodes[c].clear();
 	v->recordTop = 0;
+	for(int a = 0; a < 3; a++)
+	{
+		v->occMin[a] = 0x3FFFFFFF;
+		v->occMax[a] = -0x3FFFFFFF;
+	}
 	vol->numVoxelNodes = 0;
 	vol->numLightingRequests = 0;
 	v->requestsValid = 0;

@@ -1,0 +1,158 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol the headers declare, keeps the reference's
+struct layouts, and its HOST-side logic (file codec, voxel packing helpers, matrices, edits, picking ray) matches the
+golden fixtures produced by the reference's own code.  No kernel is launched here; frame calls must refuse to run
+without a device (there is no CPU path to fall back to)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DEMO, GOLDEN, ROOT
+
+
+def _declared_functions(header):
+    text = open(os.path.join(ROOT, "include", "DoonEngine", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(DN_[A-Za-z0-9_]+)\s*\(", text)) - {"DN_FLATTEN_INDEX", "DN_MALLOC", "DN_FREE", "DN_REALLOC"})
+
+
+def test_library_exports_every_declared_symbol(dn):
+    L = dn.lib()
+    names = _declared_functions("voxel.h") + _declared_functions("b200.h")
+    assert len(_declared_functions("voxel.h")) == 30  # the reference's 30 entry points (voxel.h:156-371)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert C.c_void_p.in_dll(L, "g_DN_message_callback") is not None
+    # every prototype the Python host declares exists too
+    assert not [n for n in dn._PROTOTYPES if not hasattr(L, n)]
+
+
+def test_struct_layouts_match_reference(dn):
+    # sizes measured on the reference's structs: DNvolume 232, DNchunk 4120, DNvoxel 20, ...
+    assert C.sizeof(dn.DNvolume) == 232
+    assert C.sizeof(dn.DNvoxel) == 20
+    assert C.sizeof(dn.DNcompressedVoxel) == 8
+    assert C.sizeof(dn.DNmat4) == 64
+    assert dn.HOST_CHUNK_DT.itemsize == 4120 and dn.HOST_HANDLE_DT.itemsize == 8 and dn.MATERIAL_DT.itemsize == 32
+    assert dn.DNvolume.camPos.offset == 112 and dn.DNvolume.skyGradientBot.offset == 200 and dn.DNvolume.frameNum.offset == 224
+
+
+def test_no_device_means_no_frame(dn):
+    """host-only volumes can be edited, loaded and saved, but nothing is drawn or lit without CUDA."""
+    if dn.lib().DN_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError):
+        dn.Engine(map_size=(2, 2, 2))  # DN_init fails: no silent fallback
+    e = dn.Engine(map_size=(2, 2, 2), host_only=True)
+    dn.messages(clear=True)
+    e.sync(dn.DN_READ_WRITE, 1)
+    e.update_lighting(1, 1000, 1.0)
+    fatal = [m for m in dn.messages() if m[1] == "FATAL"]
+    assert len(fatal) >= 2 and "no CPU path" in fatal[0][2]
+    assert e.L.DN_b200_create_framebuffer(64, 64) == 0
+    e.close()
+
+
+def test_voxvol_codec_roundtrip(dn, tmp_path):
+    """DN_load_volume parses the reference's bundled map; DN_save_volume re-creates it byte for byte."""
+    e = dn.Engine(voxvol=DEMO, min_chunks=256, host_only=True)
+    assert e.map_size == (10, 3, 10)
+    ch = e.host_chunks()
+    used = ch["pos"][:, 0] >= 0
+    assert int(used.sum()) == 240 and int(ch["numVoxels"][used].sum()) == 28776
+    p = e.get_params()
+    assert p["camFOV"] == 90.0 and p["diffuseBounceLimit"] == 5 and p["specBounceLimit"] == 2
+    out = str(tmp_path / "copy.voxvol")
+    assert e.L.DN_save_volume(out.encode(), e.vol)
+    assert open(out, "rb").read() == open(DEMO, "rb").read()
+    e.close()
+    # missing file: NULL + FILE_IO message
+    dn.messages(clear=True)
+    with pytest.raises(RuntimeError):
+        dn.Engine(voxvol=str(tmp_path / "nope.voxvol"), host_only=True)
+    assert any(m[0] == "FILE_IO" and m[1] == "ERROR" for m in dn.messages())
+
+
+def test_compress_decompress_known_answers(dn):
+    g = np.load(os.path.join(GOLDEN, "codec_kat.npz"))
+    L = dn.lib()
+    for n, m, c, want, back in zip(g["normals"], g["materials"], g["colors"], g["compressed"], g["decompressed_normals"]):
+        cv = L.DN_compress_voxel(dn.DNvoxel(int(m), dn.DNvec3(*[float(x) for x in n]), dn.DNcolor(*[int(x) for x in c])))
+        assert (cv.normal, cv.albedo) == (int(want[0]), int(want[1]))
+        d = L.DN_decompress_voxel(cv)
+        assert np.array_equal(np.array([d.normal.x, d.normal.y, d.normal.z], np.float32).view(np.uint32), back.view(np.uint32))
+        assert (d.material, d.albedo.r, d.albedo.g, d.albedo.b) == (int(m), int(c[0]), int(c[1]), int(c[2]))
+
+
+def test_matrices_bit_identical_to_reference(dn):
+    """view / projection of the demo camera vs the reference's own QuickMath results stored in the golden file."""
+    g = np.load(os.path.join(GOLDEN, "demo_frames.npz"))
+    e = dn.Engine(voxvol=DEMO, min_chunks=256, host_only=True)
+    view, proj = e.view_projection_arrays(192 / 320)
+    assert np.array_equal(view.view(np.uint32), g["view"].view(np.uint32))
+    assert np.array_equal(proj.view(np.uint32), g["proj"].view(np.uint32))
+    e.close()
+
+
+def test_edit_bookkeeping(dn):
+    """DN_set_compressed_voxel / DN_remove_voxel: automatic chunk creation and release, counts, dirty flags (voxel.c:1126-1182)."""
+    e = dn.Engine(map_size=(3, 2, 3), min_chunks=1, host_only=True)
+    L, vol = e.L, e.vol
+    solid = dn.DNcompressedVoxel(0x007F7F7F, 0x80808000)
+    empty = dn.DNcompressedVoxel(0xFFFFFFFF, 0)
+    mp = dn.DNivec3(1, 0, 2)
+    L.DN_set_compressed_voxel(vol, mp, dn.DNivec3(0, 0, 0), empty)  # empty into empty tile: no chunk
+    assert not L.DN_does_chunk_exist(vol, mp)
+    L.DN_set_compressed_voxel(vol, mp, dn.DNivec3(3, 4, 5), solid)
+    assert L.DN_does_chunk_exist(vol, mp) and L.DN_does_voxel_exist(vol, mp, dn.DNivec3(3, 4, 5))
+    ci = int(e.host_map()["chunkIndex"][1 + 3 * (0 + 2 * 2)])
+    assert int(e.host_chunks()["numVoxels"][ci]) == 1 and int(e.host_chunks()["updated"][ci]) == 1
+    assert tuple(e.host_chunks()["pos"][ci]) == (1, 0, 2)
+    got = L.DN_get_compressed_voxel(vol, mp, dn.DNivec3(3, 4, 5))
+    assert (got.normal, got.albedo) == (0x007F7F7F, 0x80808000)
+    # a second tile forces the chunk array to grow (chunkCap 1 -> 2) with a NOTE message
+    dn.messages(clear=True)
+    L.DN_set_compressed_voxel(vol, dn.DNivec3(0, 1, 0), dn.DNivec3(0, 0, 0), solid)
+    assert vol.contents.chunkCap == 2 and any(m[1] == "NOTE" and "chunk memory" in m[2] for m in dn.messages())
+    # removing the last voxel releases the chunk
+    L.DN_remove_voxel(vol, mp, dn.DNivec3(3, 4, 5))
+    assert not L.DN_does_chunk_exist(vol, mp)
+    L.DN_remove_voxel(vol, mp, dn.DNivec3(3, 4, 5))  # no chunk: must be a no-op, not a crash
+    assert L.DN_in_map_bounds(vol, dn.DNivec3(2, 1, 2)) and not L.DN_in_map_bounds(vol, dn.DNivec3(3, 0, 0)) and not L.DN_in_map_bounds(vol, dn.DNivec3(0, -1, 0))
+    assert L.DN_in_chunk_bounds(dn.DNivec3(7, 7, 7)) and not L.DN_in_chunk_bounds(dn.DNivec3(8, 0, 0))
+    mpos, cpos = dn.DNivec3(), dn.DNivec3()
+    L.DN_separate_position(dn.DNivec3(17, 9, 63), C.byref(mpos), C.byref(cpos))
+    assert (mpos.x, mpos.y, mpos.z, cpos.x, cpos.y, cpos.z) == (2, 1, 7, 1, 1, 7)
+    e.close()
+
+
+def test_step_map_picking_ray(dn):
+    """DN_step_map (CPU picking, voxel.c:1195-1272): hits the first solid voxel along the ray, reports the face normal."""
+    e = dn.Engine(map_size=(4, 4, 4), min_chunks=4, host_only=True)
+    L, vol = e.L, e.vol
+    L.DN_set_compressed_voxel(vol, dn.DNivec3(2, 1, 1), dn.DNivec3(3, 2, 1), dn.DNcompressedVoxel(0x057F7F7F, 0x11223300))
+    hit_pos, hit_normal, hit_voxel = dn.DNivec3(), dn.DNivec3(), dn.DNvoxel()
+    ok = L.DN_step_map(vol, dn.DNvec3(1.0, 0.0, 0.0), dn.DNvec3(0.05, 1.3, 1.2), 200, C.byref(hit_pos), C.byref(hit_voxel), C.byref(hit_normal))
+    assert ok and (hit_pos.x, hit_pos.y, hit_pos.z) == (19, 10, 9)
+    assert (hit_normal.x, hit_normal.y, hit_normal.z) == (-1, 0, 0)
+    assert hit_voxel.material == 5 and (hit_voxel.albedo.r, hit_voxel.albedo.g, hit_voxel.albedo.b) == (0x11, 0x22, 0x33)
+    ok = L.DN_step_map(vol, dn.DNvec3(0.0, 1.0, 0.0), dn.DNvec3(0.05, 0.3, 1.2), 200, C.byref(hit_pos), C.byref(hit_voxel), C.byref(hit_normal))
+    assert not ok
+    d = L.DN_cam_dir(dn.DNvec3(0.0, 90.0, 0.0))
+    assert abs(d.x - 1.0) < 1e-6 and abs(d.y) < 1e-6 and abs(d.z) < 1e-6
+    e.close()
+
+
+def test_set_map_size_keeps_overlap(dn):
+    e = dn.Engine(map_size=(4, 2, 4), min_chunks=8, host_only=True)
+    L, vol = e.L, e.vol
+    solid = dn.DNcompressedVoxel(0x007F7F7F, 0x80808000)
+    L.DN_set_compressed_voxel(vol, dn.DNivec3(1, 1, 1), dn.DNivec3(0, 0, 0), solid)
+    L.DN_set_compressed_voxel(vol, dn.DNivec3(3, 0, 3), dn.DNivec3(0, 0, 0), solid)
+    assert L.DN_set_map_size(vol, dn.DNuvec3(2, 2, 2))
+    assert L.DN_does_chunk_exist(vol, dn.DNivec3(1, 1, 1))
+    assert not L.DN_in_map_bounds(vol, dn.DNivec3(3, 0, 3))
+    assert int((e.host_chunks()["pos"][:, 0] >= 0).sum()) == 1  # the chunk outside the new box was dropped
+    e.close()
