@@ -223,17 +223,6 @@ def run_reference(args, scene, tiles, res, desc):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-class DevicePtr:
-    """exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
-
-
-def as_tensor(torch, ptr, nbytes, device):
-    return torch.as_tensor(DevicePtr(ptr, nbytes), device=device)
-
-
 def run_ours(args, scene, tiles, res, desc):
     import torch
     import torch.distributed as dist
@@ -266,8 +255,8 @@ def run_ours(args, scene, tiles, res, desc):
     e.sync(dn.DN_WRITE, 1)
     e.synchronize()
     t_build = time.perf_counter() - t_build
-    if world > 1:
-        L.DN_b200_set_shard(e.vol, rank, world)
+    from doonengine_b200.multigpu import ShardedEngine
+    sh = ShardedEngine(e, rank, world, torch, dist, device)  # N = 1: plain DN_draw / light phases, no collectives
 
     fb = e.framebuffer(w, h)
     fb_bytes = w * h * 16
@@ -281,56 +270,22 @@ def run_ours(args, scene, tiles, res, desc):
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    def exchange_draw():
-        """N > 1: all-gather the framebuffer bands and OR the visible bitmaps of all ranks."""
-        band_bytes = band_rows * 16 * w * 16
-        fb_t = as_tensor(torch, L.DN_b200_framebuffer_device_ptr(fb), fb_bytes, device)
-        padded = torch.empty(band_bytes * world, dtype=torch.uint8, device=device)
-        lo = min(fb_bytes, rank * band_bytes)
-        hi_ = min(fb_bytes, (rank + 1) * band_bytes)
-        mine = padded[rank * band_bytes:(rank + 1) * band_bytes]
-        mine[:hi_ - lo].copy_(fb_t[lo:hi_])
-        dist.all_gather_into_tensor(padded, mine.clone())
-        fb_t.copy_(padded[:fb_bytes])
-        vis = as_tensor(torch, L.DN_b200_array_device_ptr(e.vol, dn.ARRAY_VISIBLE), words * 4, device)
-        allvis = torch.empty(words * 4 * world, dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(allvis, vis.clone())
-        for r in range(world):
-            if r != rank:
-                L.DN_b200_or_visible(e.vol, allvis[r * words * 4:(r + 1) * words * 4].data_ptr())
-
-    def exchange_light():
-        """N > 1: all-gather the lit words (each rank computed its contiguous slice of the request list)."""
-        slice_bytes = L.DN_b200_staging_slice_bytes(e.vol)
-        if slice_bytes == 0:
-            return
-        st = as_tensor(torch, L.DN_b200_array_device_ptr(e.vol, dn.ARRAY_STAGING), slice_bytes * world, device)
-        dist.all_gather_into_tensor(st, st[rank * slice_bytes:(rank + 1) * slice_bytes].clone())
-
     def step(k, timed, read_back):
         """one frame; returns the events bracketing its phases."""
         marks = [ev() for _ in range(6)] if timed else None
         if timed:
             marks[0].record(stream)
-        L.DN_draw(e.vol, fb, view, proj, -1, -1)
-        if world > 1:
-            exchange_draw()
+        sh.draw(fb, view, proj)
         if timed:
             marks[1].record(stream)
         L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
         if timed:
             marks[2].record(stream)
-        if world > 1:
-            L.DN_b200_light_compute(e.vol, 1, 1000, C.c_float(frame_time(k)))
-            if timed:
-                marks[3].record(stream)
-            exchange_light()
-            L.DN_b200_light_commit(e.vol)
-        else:
-            L.DN_b200_light_compute(e.vol, 1, 1000, C.c_float(frame_time(k)))
-            if timed:
-                marks[3].record(stream)
-            L.DN_b200_light_commit(e.vol)
+        sh.light_compute(1, 1000, frame_time(k))
+        if timed:
+            marks[3].record(stream)
+        sh.light_exchange()
+        sh.light_commit()
         if timed:
             marks[4].record(stream)
         if read_back:
@@ -399,20 +354,17 @@ def run_ours(args, scene, tiles, res, desc):
     if rank == 0:
         e.enable_counters(True)
         e.counters(reset=True)
-        L.DN_draw(e.vol, fb, view, proj, -1, -1)
-        if world > 1:
-            pass  # counters of rank 0's band only; the draw roofline is reported for N = 1
-        cd = e.counters(reset=True)
-    if world > 1:
-        exchange_draw()
+        sh.draw(fb, view, proj)
+        cd = e.counters(reset=True)  # N > 1: rank 0's band only; the draw roofline is reported for N = 1
+    else:
+        sh.draw(fb, view, proj)
     L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
     r_count = int(e.vol.contents.numLightingRequests)
-    L.DN_b200_light_compute(e.vol, 1, 1000, C.c_float(frame_time(args.warmup + 2 * args.steps)))
+    sh.light_compute(1, 1000, frame_time(args.warmup + 2 * args.steps))
     if rank == 0:
         cl = e.counters(reset=True)
-    if world > 1:
-        exchange_light()
-    L.DN_b200_light_commit(e.vol)
+    sh.light_exchange()
+    sh.light_commit()
     e.synchronize()
     if rank == 0:
         e.enable_counters(False)

@@ -102,7 +102,7 @@ SLOT_DT = np.dtype([("mask", "<u4", 16), ("voxelBase", "<u4"), ("numVoxels", "<u
 HIT_DT = np.dtype([("status", "<i4"), ("mapIndex", "<u4"), ("localIndex", "<u4"), ("recordIndex", "<u4")])
 assert HOST_CHUNK_DT.itemsize == 4120 and HOST_HANDLE_DT.itemsize == 8 and MATERIAL_DT.itemsize == 32 and SLOT_DT.itemsize == 128
 
-ARRAY_TILE_SLOTS, ARRAY_VISIBLE, ARRAY_SLOTS, ARRAY_RECORDS, ARRAY_REQUESTS, ARRAY_STAGING = range(6)
+ARRAY_TILE_SLOTS, ARRAY_VISIBLE, ARRAY_SLOTS, ARRAY_RECORDS, ARRAY_REQUESTS, ARRAY_STAGING, ARRAY_PROPAGATE = range(7)
 DN_READ, DN_WRITE, DN_READ_WRITE = 0, 1, 2
 
 PARAM_NAMES = ("camPos", "camOrient", "camFOV", "camViewMode", "sunDir", "sunStrength", "ambientLightStrength",
@@ -167,7 +167,7 @@ _PROTOTYPES = {
     "DN_b200_light_compute": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int, C.c_float]),
     "DN_b200_light_commit": (C.c_bool, [C.POINTER(DNvolume)]),
     "DN_b200_staging_slice_bytes": (C.c_size_t, [C.POINTER(DNvolume)]),
-    "DN_b200_or_visible": (C.c_bool, [C.POINTER(DNvolume), C.c_void_p]),
+    "DN_b200_or_bitmap": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_void_p]),
 }
 
 _lib = None

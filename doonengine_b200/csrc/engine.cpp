@@ -1038,6 +1038,7 @@ static bool array_info(VolumeImpl* v, DNb200array which, void** ptr, size_t* byt
 	case DN_B200_SLOTS:      *ptr = v->slots.ptr;    *bytes = (size_t)v->slotTop * sizeof(DnbSlot); return true;
 	case DN_B200_RECORDS:    *ptr = v->records.ptr;  *bytes = v->recordTop * sizeof(uint4); return true;
 	case DN_B200_REQUESTS:   *ptr = v->requests.ptr; *bytes = v->requestsValid * sizeof(uint32_t); return true;
+	case DN_B200_PROPAGATE:  *ptr = v->propagate.ptr; *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
 	case DN_B200_STAGING:
 	{
 		const size_t per = (v->stagedRequests + v->shardWorld - 1) / v->shardWorld;
@@ -1147,11 +1148,12 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 
 extern "C" cudaError_t dnb_launch_or_bits(uint32_t* dst, const uint32_t* src, uint32_t words, cudaStream_t stream);
 
-extern "C" bool DN_b200_or_visible(DNvolume* vol, const void* deviceBitmap)
+extern "C" bool DN_b200_or_bitmap(DNvolume* vol, DNb200array which, const void* deviceBitmap)
 {
 	VolumeImpl* v = impl_of(vol);
-	if(!device_ready(v, "DN_b200_or_visible"))
+	if(!device_ready(v, "DN_b200_or_bitmap") || (which != DN_B200_VISIBLE && which != DN_B200_PROPAGATE))
 		return false;
 	const uint32_t words = (uint32_t)((num_tiles(vol) + 31) / 32);
-	return cuda_ok(dnb_launch_or_bits(v->visible.ptr, (const uint32_t*)deviceBitmap, words, ctx().stream()), "visible merge");
+	uint32_t* dst = which == DN_B200_VISIBLE ? v->visible.ptr : v->propagate.ptr;
+	return cuda_ok(dnb_launch_or_bits(dst, (const uint32_t*)deviceBitmap, words, ctx().stream()), "bitmap merge");
 }

@@ -51,7 +51,8 @@ typedef enum DNb200array
 	DN_B200_SLOTS      = 2, /* 128-byte chunk slots (csrc/layout.h DnbSlot), slot-cap entries */
 	DN_B200_RECORDS    = 3, /* 16-byte voxel records, record-cap entries */
 	DN_B200_REQUESTS   = 4, /* uint32 request words of the last reading sync */
-	DN_B200_STAGING    = 5  /* 96 uint32 per request: the lit words of the last lighting compute phase */
+	DN_B200_STAGING    = 5, /* 96 uint32 per request: the lit words of the last lighting compute phase */
+	DN_B200_PROPAGATE  = 6  /* uint32 words, 1 bit per tile: visible bits raised by specular hits, merged at commit */
 } DNb200array;
 size_t DN_b200_array_bytes(DNvolume* vol, DNb200array which);
 size_t DN_b200_download(DNvolume* vol, DNb200array which, void* dst, size_t dstBytes);
@@ -83,12 +84,14 @@ void DN_b200_rescan(DNvolume* vol); /* marks every tile touched: the next writin
 /* this process lights requests [rank*ceil(R/world), ...) and draws the rank-th band of 16-pixel rows */
 bool DN_b200_set_shard(DNvolume* vol, int rank, int worldSize);
 /* DN_update_lighting == light_compute + light_commit.  Between the two, a sharded host all-gathers the staging
- * array (DN_B200_STAGING; each rank's slice is DN_b200_staging_slice_bytes() long at rank*that offset). */
+ * array (DN_B200_STAGING; each rank's slice is DN_b200_staging_slice_bytes() long at rank*that offset) and ORs
+ * the ranks' DN_B200_PROPAGATE bitmaps together. */
 bool   DN_b200_light_compute(DNvolume* vol, int numDiffuseSamples, int maxDiffuseSamples, float time);
 bool   DN_b200_light_commit(DNvolume* vol);
 size_t DN_b200_staging_slice_bytes(DNvolume* vol);
-/* visible[] |= other[] for a bitmap gathered from another rank (device pointer, same length) */
-bool   DN_b200_or_visible(DNvolume* vol, const void* deviceBitmap);
+/* bitmap[] |= other[] for a bitmap gathered from another rank (device pointer, same length); `which` is
+ * DN_B200_VISIBLE (after a sharded draw) or DN_B200_PROPAGATE (after a sharded lighting compute phase) */
+bool   DN_b200_or_bitmap(DNvolume* vol, DNb200array which, const void* deviceBitmap);
 
 #ifdef __cplusplus
 }

@@ -738,6 +738,23 @@ void orh_update_lighting(OrhVolume* v, int numDiffuseSamples, int maxDiffuseSamp
 	orb_light(&b, &u, v->requests, v->numRequests, v->voxelCap, &v->lightCounters);
 }
 
+/* the same dispatch in two phases over a request range (see orb_light_compute / orb_light_commit) */
+void orh_light_compute(OrhVolume* v, int numDiffuseSamples, int maxDiffuseSamples, float time, size_t first, size_t count, uint32_t* staging, uint8_t* propagate)
+{
+	OrbUniforms u;
+	orh_light_uniforms(v, numDiffuseSamples, maxDiffuseSamples, time, &u);
+	OrbBuffers b = buffers_of(v);
+	orb_light_compute(&b, &u, v->requests, first, count, staging, propagate, &v->lightCounters);
+}
+
+void orh_light_commit(OrhVolume* v, const uint32_t* staging, const uint8_t* propagate)
+{
+	OrbUniforms u;
+	common_uniforms(v, &u);
+	OrbBuffers b = buffers_of(v);
+	orb_light_commit(&b, &u, v->requests, v->numRequests, staging, propagate);
+}
+
 /* accessors for ctypes */
 OrbHandle*   orh_map(OrhVolume* v)            { return v->map; }
 OrbChunk*    orh_gpu_chunks(OrhVolume* v)     { return v->gchunks; }

@@ -131,6 +131,11 @@ void orb_draw(const OrbBuffers* buf, const OrbUniforms* u, int w, int h, float* 
  * and map[].flags in place. */
 void orb_light(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t numRequests, size_t numVoxelRecords, OrbCounters* counters);
 
+/* the two phases orb_light is made of, exposed so that a dispatch can be split over request ranges (multi-GPU
+ * sharding emulation in tests/): compute writes 96 staged words per request and ORs propagate[]; commit applies. */
+void orb_light_compute(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t first, size_t count, uint32_t* staging, uint8_t* propagate, OrbCounters* counters);
+void orb_light_commit(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t numRequests, const uint32_t* staging, const uint8_t* propagate);
+
 /* helpers exposed for unit tests */
 uint32_t orb_get_voxel_index(const OrbBuffers* buf, uint32_t mapIndex, int x, int y, int z);
 void     orb_get_voxel_position(const OrbBuffers* buf, uint32_t chunk, uint32_t voxNum, int out[3]);

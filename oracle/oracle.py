@@ -183,6 +183,8 @@ class OracleEngine(_EngineBase):
         L.orh_draw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orh_update_lighting.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
         L.orh_get_params.argtypes = [C.c_void_p, C.c_void_p]
+        L.orh_light_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.orh_light_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orh_set_params.argtypes = [C.c_void_p, C.c_void_p]
         L.orh_draw_uniforms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orh_light_uniforms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
@@ -258,6 +260,13 @@ class OracleEngine(_EngineBase):
 
     def update_lighting(self, num_diffuse=1, max_diffuse=1000, time=1.0):
         self.L.orh_update_lighting(self.v, num_diffuse, max_diffuse, C.c_float(time))
+
+    def light_compute(self, num_diffuse, max_diffuse, time, first, count, staging, propagate):
+        """phase 1 over requests [first, first+count): fills staging (uint32[96*R]) and ORs propagate (uint8[tiles])."""
+        self.L.orh_light_compute(self.v, num_diffuse, max_diffuse, C.c_float(time), first, count, staging.ctypes.data, propagate.ctypes.data)
+
+    def light_commit(self, staging, propagate):
+        self.L.orh_light_commit(self.v, staging.ctypes.data, propagate.ctypes.data)
 
     def draw_uniforms(self, aspect):
         view, proj = self.view_projection(aspect)

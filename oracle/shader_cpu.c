@@ -705,7 +705,6 @@ static void diffuse_ray(Inv* inv, v3 normal, v3 rayPos, Voxel initialVoxel, floa
 typedef struct
 {
 	uint32_t live;
-	uint32_t recordIndex;
 	uint32_t w1, w2, w3;
 } LightOut;
 
@@ -787,7 +786,6 @@ static void light_invocation(Inv* inv, uint32_t request, uint32_t lane, LightOut
 	uint32_t wz = (uint32_t)rintf(diffuseLight.z * 65535.0f);
 
 	out->live = 1;
-	out->recordIndex = voxelIndex;
 	out->w1 = encode_uint_RGBA((uint32_t)rintf(thisVoxel.albedo.x * 255.0f), (uint32_t)rintf(thisVoxel.albedo.y * 255.0f), (uint32_t)rintf(thisVoxel.albedo.z * 255.0f), (uint32_t)rintf(specLight.x * 255.0f));
 	out->w2 = encode_uint_RGBA((uint32_t)rintf(specLight.y * 255.0f), (uint32_t)rintf(specLight.z * 255.0f), (wx >> 8) & 0xFF, wx & 0xFF);
 	out->w3 = encode_uint_RGBA((wy >> 8) & 0xFF, wy & 0xFF, (wz >> 8) & 0xFF, wz & 0xFF);
@@ -799,14 +797,15 @@ static void counters_add(OrbCounters* d, const OrbCounters* s)
 	d->records += s->records; d->voxelsLit += s->voxelsLit; d->pixels += s->pixels;
 }
 
-void orb_light(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t numRequests, size_t numVoxelRecords, OrbCounters* counters)
+/* Phase 1 of a lighting dispatch: the invocations of requests [first, first+count) are evaluated against the
+ * UNMODIFIED buffers (N1, N2) and their packed words are written to `staging` -- 96 words per request, indexed from
+ * request 0: [32 x albedo|spec.x][32 x spec.yz|diffuse.x][32 x diffuse.yz], zero for dead lanes -- the same layout
+ * the CUDA path stages (doonengine_b200/csrc/light.cu).  Visible-bit propagations (LI:101-105) are OR-ed into
+ * `propagate` (one byte per tile).  Nothing in `buf` is written except map[].lastUsed (N4). */
+void orb_light_compute(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t first, size_t count, uint32_t* staging, uint8_t* propagate, OrbCounters* counters)
 {
-	(void)numVoxelRecords;
 	size_t numTiles = (size_t)u->mapSize[0] * u->mapSize[1] * u->mapSize[2];
-	LightOut* outs = (LightOut*)malloc(sizeof(LightOut) * 32 * (numRequests ? numRequests : 1));
 	uint8_t* visibleSnapshot = (uint8_t*)malloc(numTiles ? numTiles : 1);
-	uint8_t* propagate = (uint8_t*)calloc(numTiles ? numTiles : 1, 1);
-
 	for(size_t i = 0; i < numTiles; i++)
 		visibleSnapshot[i] = (buf->map[i].flags & 4) ? 1 : 0;
 
@@ -824,42 +823,66 @@ void orb_light(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requ
 		inv.visibleSnapshot = visibleSnapshot;
 
 		#pragma omp for schedule(dynamic, 4)
-		for(size_t r = 0; r < numRequests; r++)
+		for(size_t r = first; r < first + count; r++)
 			for(uint32_t lane = 0; lane < 32; lane++)
-				light_invocation(&inv, requests[r], lane, &outs[r * 32 + lane]);
+			{
+				LightOut o;
+				light_invocation(&inv, requests[r], lane, &o);
+				staging[r * 96 + lane]      = o.live ? o.w1 : 0;
+				staging[r * 96 + 32 + lane] = o.live ? o.w2 : 0;
+				staging[r * 96 + 64 + lane] = o.live ? o.w3 : 0;
+			}
 
 		#pragma omp critical
 		counters_add(&total, &inv.c);
 	}
 
-	/* commit (N1-N3): records, then visible-bit clears, sample counts, then propagation */
+	if(counters)
+		counters_add(counters, &total);
+	free(visibleSnapshot);
+}
+
+/* Phase 2: commit (N1-N3) -- records, then visible-bit clears and sample counts, then propagation.
+ * A lane is live iff its voxel number is below the chunk's surface-voxel count (get_voxel_position, SH:220-223). */
+void orb_light_commit(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t numRequests, const uint32_t* staging, const uint8_t* propagate)
+{
+	size_t numTiles = (size_t)u->mapSize[0] * u->mapSize[1] * u->mapSize[2];
 	for(size_t r = 0; r < numRequests; r++)
 	{
 		uint32_t mapIndex = requests[r] >> 4;
+		uint32_t numVoxels = 0;
+		for(int i = 0; i < 16; i++)
+			numVoxels += (uint32_t)__builtin_popcount(buf->chunks[mapIndex].bitMask[i]);
 		for(uint32_t lane = 0; lane < 32; lane++)
 		{
-			const LightOut* o = &outs[r * 32 + lane];
-			if(!o->live)
+			uint32_t voxNum = lane + (requests[r] & 15) * 32;
+			if(voxNum >= numVoxels)
 				continue;
 
-			buf->voxels[o->recordIndex].albedo = o->w1;
-			buf->voxels[o->recordIndex].specLight = o->w2;
-			buf->voxels[o->recordIndex].diffuseLight = o->w3;
+			uint32_t recordIndex = buf->map[mapIndex].voxelIndex + voxNum;
+			buf->voxels[recordIndex].albedo = staging[r * 96 + lane];            /* LI:276 */
+			buf->voxels[recordIndex].specLight = staging[r * 96 + 32 + lane];    /* LI:277 */
+			buf->voxels[recordIndex].diffuseLight = staging[r * 96 + 64 + lane]; /* LI:278 */
 
 			buf->map[mapIndex].flags &= ~4u;                 /* LI:281 */
-			if(lane == 0 && (requests[r] & 15) == 0)
+			if(voxNum == 0)
 				buf->chunks[mapIndex].numIndirectSamples++;  /* LI:284-285 */
 		}
 	}
 	for(size_t i = 0; i < numTiles; i++)
 		if(propagate[i])
 			buf->map[i].flags |= 4u;                         /* LI:104-105 */
+}
 
-	if(counters)
-		counters_add(counters, &total);
-
-	free(outs);
-	free(visibleSnapshot);
+void orb_light(const OrbBuffers* buf, const OrbUniforms* u, const uint32_t* requests, size_t numRequests, size_t numVoxelRecords, OrbCounters* counters)
+{
+	(void)numVoxelRecords;
+	size_t numTiles = (size_t)u->mapSize[0] * u->mapSize[1] * u->mapSize[2];
+	uint32_t* staging = (uint32_t*)malloc(sizeof(uint32_t) * 96 * (numRequests ? numRequests : 1));
+	uint8_t* propagate = (uint8_t*)calloc(numTiles ? numTiles : 1, 1);
+	orb_light_compute(buf, u, requests, 0, numRequests, staging, propagate, counters);
+	orb_light_commit(buf, u, requests, numRequests, staging, propagate);
+	free(staging);
 	free(propagate);
 }
 

@@ -225,3 +225,114 @@ def test_empty_map_and_odd_sizes(dn, oracle_mod):
     e.synchronize()
     e.close()
     o.close()
+
+
+def test_sharded_equals_unsharded(dn, oracle_mod):
+    """SURVEY.md 8e determinism requirement on the device: two replicas on one GPU act as rank 0 and rank 1 of a
+    2-way shard (band draw, request-slice lighting, staged-word / bitmap exchange done with device copies); after every
+    frame both replicas must be bit-identical to an unsharded engine and to the oracle."""
+    import torch
+    from doonengine_b200 import multigpu, scenes
+    tiles = (6, 4, 6)
+    world = 2
+    device = torch.device("cuda", 0)
+    reps = [dn.Engine(map_size=tiles, min_chunks=64) for _ in range(world)]
+    whole = dn.Engine(map_size=tiles, min_chunks=64)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    for eng in reps + [whole, o]:
+        scenes.build(eng, scenes.mixed_materials(tiles), **scenes.mixed_camera(tiles))
+        eng.sync(1, 1)
+    L = whole.L
+    for r, e in enumerate(reps):
+        assert L.DN_b200_set_shard(e.vol, r, world)
+
+    def tensor(e, which):
+        n = L.DN_b200_array_bytes(e.vol, which)
+        return torch.as_tensor(multigpu._DevicePtr(L.DN_b200_array_device_ptr(e.vol, which), n), device=device) if n else None
+
+    w, h = W, H
+    rows = h // 16
+    for k in range(4):
+        # --- draw: each replica its band, then exchange bands and visible bits ---
+        fbs = []
+        for e in reps:
+            fb = e.framebuffer(w, h)
+            L.DN_b200_clear_framebuffer(fb, 0.0)
+            e.draw_async(w, h)
+            fbs.append(fb)
+        for e in reps:
+            e.synchronize()
+        imgs = [torch.as_tensor(multigpu._DevicePtr(L.DN_b200_framebuffer_device_ptr(fb), w * h * 16), device=device) for fb in fbs]
+        for r in range(world):
+            b0, b1, _ = multigpu.row_band(rows, r, world)
+            lo, hi = b0 * 16 * w * 16, b1 * 16 * w * 16
+            for q in range(world):
+                if q != r:
+                    imgs[q][lo:hi].copy_(imgs[r][lo:hi])
+        vis = [tensor(e, dn.ARRAY_VISIBLE).clone() for e in reps]
+        torch.cuda.synchronize()
+        for r, e in enumerate(reps):
+            for q in range(world):
+                if q != r:
+                    assert L.DN_b200_or_bitmap(e.vol, dn.ARRAY_VISIBLE, vis[q].data_ptr())
+        ref_img = whole.draw(w, h)
+        for r, e in enumerate(reps):
+            e.synchronize()
+            got = e.read_framebuffer(fbs[r])
+            assert np.array_equal(got.view(np.uint32), ref_img.view(np.uint32)), "frame %d: image of replica %d differs from the unsharded draw" % (k, r)
+        assert_images_close(ref_img, o.draw(w, h), "frame %d" % k)
+
+        # --- sync: identical request lists everywhere ---
+        for eng in reps + [whole, o]:
+            eng.sync(2, 1)
+        want = o.requests()
+        for eng in reps + [whole]:
+            assert np.array_equal(eng.requests(), want)
+
+        # --- lighting: compute slices, exchange staged words + propagate bits, commit ---
+        for e in reps:
+            assert L.DN_b200_light_compute(e.vol, 1, 1000, frame_time(k))
+            e.synchronize()
+        slice_bytes = L.DN_b200_staging_slice_bytes(reps[0].vol)
+        if slice_bytes:
+            st = [tensor(e, dn.ARRAY_STAGING) for e in reps]
+            for r in range(world):
+                for q in range(world):
+                    if q != r:
+                        st[q][r * slice_bytes:(r + 1) * slice_bytes].copy_(st[r][r * slice_bytes:(r + 1) * slice_bytes])
+        prop = [tensor(e, dn.ARRAY_PROPAGATE).clone() for e in reps]
+        torch.cuda.synchronize()
+        for r, e in enumerate(reps):
+            for q in range(world):
+                if q != r:
+                    assert L.DN_b200_or_bitmap(e.vol, dn.ARRAY_PROPAGATE, prop[q].data_ptr())
+            assert L.DN_b200_light_commit(e.vol)
+        whole.update_lighting(1, 1000, frame_time(k))
+        o.update_lighting(1, 1000, frame_time(k))
+
+        ref_state = records_by_tile(whole)
+        _compare_state(whole, records_by_tile(o), "frame %d (unsharded vs oracle)" % k)
+        for r, e in enumerate(reps):
+            st_r = records_by_tile(e)
+            for key in ref_state:
+                assert np.array_equal(st_r[key], ref_state[key]), "frame %d: %s of replica %d differs from the unsharded engine" % (k, key, r)
+    for eng in reps + [whole, o]:
+        eng.close()
+
+
+def test_staging_words_match_oracle(dn, oracle_mod):
+    """the staged lit words of the compute phase (what travels between GPUs) equal the oracle's, request by request."""
+    e = dn.Engine(voxvol=DEMO, min_chunks=256)
+    o = oracle_mod.OracleEngine(voxvol=DEMO, min_chunks=256)
+    for eng in (e, o):
+        eng.sync(1, 1)
+        eng.draw(W, H)
+        eng.sync(2, 1)
+    n = len(o.requests())
+    assert e.L.DN_b200_light_compute(e.vol, 1, 1000, 1.0)
+    got = e.download(dn.ARRAY_STAGING, np.uint32)
+    want = np.zeros(n * 96, np.uint32)
+    o.light_compute(1, 1000, 1.0, 0, n, want, np.zeros(o.num_tiles(), np.uint8))
+    assert got.shape == want.shape and np.array_equal(got, want)
+    e.close()
+    o.close()
