@@ -151,6 +151,8 @@ _PROTOTYPES = {
     "DN_b200_framebuffer_device_ptr": (C.c_void_p, [C.c_uint32]),
     "DN_b200_read_framebuffer": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
     "DN_b200_clear_framebuffer": (C.c_bool, [C.c_uint32, C.c_float]),
+    "DN_b200_read_framebuffer_async": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
+    "DN_b200_wait_framebuffer": (C.c_bool, []),
     "DN_b200_capture_hits": (C.c_bool, [C.c_uint32, C.c_bool]),
     "DN_b200_read_hits": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
     "DN_b200_fetch_lighting_requests": (C.c_size_t, [C.POINTER(DNvolume)]),

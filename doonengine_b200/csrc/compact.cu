@@ -8,10 +8,9 @@
  *
  * Input is the 1-bit-per-tile visible bitmap, so a 2048^3-voxel map (16.7 M tiles) is a 2 MB scan instead of
  * a 201 MB handle read-back.  Three launches:
- *   dn_compact_kernel<false>  each warp owns 32 bitmap words (1024 tiles): coalesced word load, then for every
- *                             non-zero word lane l tests bit l (warp ballot order = tile order), gathers the
- *                             slot's voxel count, and a shuffle prefix sum gives the per-word request count.
- *                             Per-CTA totals go to blockCounts[].
+ *   dn_compact_kernel<false>  one thread per tile, one warp per bitmap word: lane l tests bit l (lane order = tile
+ *                             order), gathers the slot's voxel count, and a shuffle prefix sum gives the per-word
+ *                             request count.  Per-CTA totals (256 tiles) go to blockCounts[].
  *   dn_scan_blocks_kernel     one CTA: exclusive scan of blockCounts[] and the grand total.
  *   dn_compact_kernel<true>   same walk, writing the request words at their final offsets.
  * The host reads the total back in between (DNvolume::numLightingRequests is public) and grows the request
@@ -21,7 +20,7 @@
 #include "kernels.h"
 
 #define COMPACT_WARPS 8
-#define COMPACT_WORDS_PER_CTA (COMPACT_WARPS * 32)
+#define COMPACT_TILES_PER_CTA (COMPACT_WARPS * 32)
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane)
 {
@@ -35,6 +34,8 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lan
 	return v;
 }
 
+/* one thread per tile, one warp per bitmap word: every dependent gather (bitmap word -> slot id -> voxel count) of a CTA is
+ * in flight at once, so a pass costs about two memory latencies however many tiles are visible */
 template <bool WRITE>
 __global__ void __launch_bounds__(COMPACT_WARPS * 32) dn_compact_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ forced, const uint32_t* __restrict__ tileSlot,
                                                                         const DnbSlot* __restrict__ slots, uint32_t numTiles, uint32_t split, uint32_t frameNum,
@@ -43,75 +44,42 @@ __global__ void __launch_bounds__(COMPACT_WARPS * 32) dn_compact_kernel(const ui
 	__shared__ uint32_t s_warpTotal[COMPACT_WARPS];
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t numWords = (numTiles + 31) / 32;
-	const uint32_t wordIdx = (blockIdx.x * COMPACT_WARPS + warp) * 32 + lane;
-	const uint32_t myWord = wordIdx < numWords ? __ldg(visible + wordIdx) : 0u;
+	const uint32_t tile = blockIdx.x * COMPACT_TILES_PER_CTA + threadIdx.x;
+	const uint32_t word = (tile - lane) < numTiles ? __ldg(visible + (tile >> 5)) : 0u; /* same address for the whole warp */
 
-	uint32_t nonzero = __ballot_sync(0xFFFFFFFFu, myWord != 0u);
-
-	/* WRITE pass: first recompute this warp's total to know where it starts inside the CTA */
-	uint32_t total = 0;
-	for(int pass = 0; pass < (WRITE ? 2 : 1); pass++)
+	uint32_t groups = 0;
+	if(((word >> lane) & 1u) && tile < numTiles)
 	{
-		uint32_t cursor = 0;
-		if(WRITE && pass == 1)
+		const uint32_t slotId = __ldg(tileSlot + tile);
+		if(slotId != 0u)
 		{
-			if(lane == 0)
-				s_warpTotal[warp] = total;
-			__syncthreads();
-			cursor = __ldg(blockOffsets + blockIdx.x);
-			for(uint32_t w = 0; w < warp; w++)
-				cursor += s_warpTotal[w];
-		}
-
-		uint32_t todo = nonzero;
-		total = 0;
-		while(todo)
-		{
-			const int src = __ffs(todo) - 1;
-			todo &= todo - 1;
-			const uint32_t word = __shfl_sync(0xFFFFFFFFu, myWord, src);
-			const uint32_t tile = ((blockIdx.x * COMPACT_WARPS + warp) * 32 + (uint32_t)src) * 32 + lane;
-
-			uint32_t groups = 0;
-			if(((word >> lane) & 1u) && tile < numTiles)
-			{
-				const uint32_t slotId = __ldg(tileSlot + tile);
-				if(slotId != 0u)
-				{
-					bool selected = (tile % split) == frameNum;
-					if(!selected && forced)
-						selected = (__ldg(forced + (tile >> 5)) >> (tile & 31u)) & 1u;
-					if(selected)
-						groups = (__ldg(&slots[slotId - 1u].numVoxels) + 31u) / 32u;
-				}
-			}
-
-			const uint32_t incl = warp_inclusive_scan(groups, lane);
-			if(WRITE && pass == 1)
-			{
-				uint32_t at = cursor + incl - groups;
-				for(uint32_t g = 0; g < groups; g++)
-					requests[at + g] = (tile << 4) | g;
-			}
-			const uint32_t wordTotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-			cursor += wordTotal;
-			total += wordTotal;
+			bool selected = (tile % split) == frameNum;
+			if(!selected && forced)
+				selected = (__ldg(forced + (tile >> 5)) >> lane) & 1u;
+			if(selected)
+				groups = (__ldg(&slots[slotId - 1u].numVoxels) + 31u) / 32u;
 		}
 	}
 
-	if(!WRITE)
+	const uint32_t incl = warp_inclusive_scan(groups, lane);
+	if(lane == 31)
+		s_warpTotal[warp] = incl;
+	__syncthreads();
+
+	if(WRITE)
 	{
-		if(lane == 0)
-			s_warpTotal[warp] = total;
-		__syncthreads();
-		if(threadIdx.x == 0)
-		{
-			uint32_t sum = 0;
-			for(int w = 0; w < COMPACT_WARPS; w++)
-				sum += s_warpTotal[w];
-			blockCounts[blockIdx.x] = sum;
-		}
+		uint32_t at = __ldg(blockOffsets + blockIdx.x) + incl - groups;
+		for(uint32_t w = 0; w < warp; w++)
+			at += s_warpTotal[w];
+		for(uint32_t g = 0; g < groups; g++)
+			requests[at + g] = (tile << 4) | g;
+	}
+	else if(threadIdx.x == 0)
+	{
+		uint32_t sum = 0;
+		for(int w = 0; w < COMPACT_WARPS; w++)
+			sum += s_warpTotal[w];
+		blockCounts[blockIdx.x] = sum;
 	}
 }
 
@@ -182,8 +150,7 @@ extern "C" cudaError_t dnb_launch_or_bits(uint32_t* dst, const uint32_t* src, ui
 
 extern "C" uint32_t dnb_compact_num_blocks(uint32_t numTiles)
 {
-	const uint32_t numWords = (numTiles + 31) / 32;
-	return (numWords + COMPACT_WORDS_PER_CTA - 1) / COMPACT_WORDS_PER_CTA;
+	return (numTiles + COMPACT_TILES_PER_CTA - 1) / COMPACT_TILES_PER_CTA;
 }
 
 extern "C" cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets,

@@ -247,6 +247,7 @@ static void release_slot(VolumeImpl* v, uint32_t slot)
 		v->slotNodeClass[slot] = 0xFF;
 		v->pub.numVoxelNodes--;
 		v->stats.residentRecords -= v->slotNumVoxels[slot];
+		v->residentGroups -= (v->slotNumVoxels[slot] + 31) / 32;
 		v->slotNumVoxels[slot] = 0;
 	}
 }
@@ -268,6 +269,7 @@ static uint32_t acquire_node(VolumeImpl* v, uint32_t slot, uint32_t n)
 	v->slotNodeStart[slot] = start;
 	v->slotNodeClass[slot] = (uint8_t)cls;
 	v->slotNumVoxels[slot] = n;
+	v->residentGroups += (n + 31) / 32;
 	v->stats.residentRecords += n;
 	v->pub.numVoxelNodes++;
 	return start;
@@ -535,20 +537,20 @@ static void sync_read(VolumeImpl* v, uint32_t split)
 			forced = v->forced.ptr;
 	}
 
-	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, s), "compaction count");
-	cuda_ok(cudaMemcpyAsync(v->pinnedScalars, v->scalars.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "request count read-back");
-	cuda_ok(cudaStreamSynchronize(s), "compaction count");
-	const size_t total = v->pinnedScalars[0];
-
-	if(total > v->requests.cap)
+	/* the request buffer is sized for "every resident chunk visible" (the host knows that bound exactly), so the count,
+	 * scan and write passes are queued back to back and the host waits once, for the total */
+	if(v->residentGroups > v->requests.cap)
 	{
 		size_t cap = v->requests.cap ? v->requests.cap : 1024;
-		while(cap < total) cap *= 2;
+		while(cap < v->residentGroups) cap *= 2;
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing lighting request buffer to accomodate %zu requests (%zu bytes)", cap, cap * sizeof(uint32_t));
 		device_reserve(v->requests, cap, false, false, "lighting requests");
 	}
-	if(total > 0)
-		cuda_ok(dnb_launch_compact_write(&scene, forced, split, vol->frameNum, v->blockOffsets.ptr, v->requests.ptr, s), "compaction write");
+	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, s), "compaction count");
+	cuda_ok(cudaMemcpyAsync(v->pinnedScalars, v->scalars.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "request count read-back");
+	cuda_ok(dnb_launch_compact_write(&scene, forced, split, vol->frameNum, v->blockOffsets.ptr, v->requests.ptr, s), "compaction write");
+	cuda_ok(cudaStreamSynchronize(s), "compaction");
+	const size_t total = v->pinnedScalars[0];
 
 	if(forced)
 	{
@@ -619,6 +621,9 @@ extern "C" bool DN_init(void)
 
 	bool ok = cuda_ok(cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking), "stream create");
 	ok = ok && cuda_ok(cudaStreamCreateWithFlags(&c.uploadStream, cudaStreamNonBlocking), "stream create");
+	ok = ok && cuda_ok(cudaStreamCreateWithFlags(&c.readStream, cudaStreamNonBlocking), "stream create");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evDrawDone, cudaEventDisableTiming), "event create");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evReadDone, cudaEventDisableTiming), "event create");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evUploadDone, cudaEventDisableTiming), "event create");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evComputeDone, cudaEventDisableTiming), "event create");
 	ok = ok && cuda_ok(cudaEventCreate(&c.evT0), "event create") && cuda_ok(cudaEventCreate(&c.evT1), "event create");
@@ -659,6 +664,8 @@ extern "C" void DN_quit(void)
 	cudaEventDestroy(c.evUploadDone); cudaEventDestroy(c.evComputeDone); cudaEventDestroy(c.evT0); cudaEventDestroy(c.evT1);
 	cudaStreamDestroy(c.ownStream);
 	cudaStreamDestroy(c.uploadStream);
+	cudaStreamDestroy(c.readStream);
+	cudaEventDestroy(c.evDrawDone); cudaEventDestroy(c.evReadDone);
 	c.ownStream = c.uploadStream = nullptr;
 	c.ready = false;
 }
@@ -753,6 +760,29 @@ extern "C" bool DN_b200_read_framebuffer(GLuint id, float* dst, size_t bytes)
 	return cuda_ok(cudaMemcpyAsync(dst, fb->image, need, cudaMemcpyDeviceToHost, s), "framebuffer read") && cuda_ok(cudaStreamSynchronize(s), "framebuffer read");
 }
 
+/* Starts copying the framebuffer to (preferably pinned) host memory on a side stream, ordered after everything queued
+ * so far on the compute stream (i.e. after the DN_draw that produced it); later kernels overlap with the copy.
+ * DN_b200_wait_framebuffer() blocks until the copy has landed and makes later draws wait for it too. */
+extern "C" bool DN_b200_read_framebuffer_async(GLuint id, float* dst, size_t bytes)
+{
+	Framebuffer* fb = find_fb(id);
+	const size_t need = fb ? (size_t)fb->width * fb->height * sizeof(float4) : 0;
+	if(!fb || bytes < need)
+		return false;
+	Context& c = ctx();
+	bool ok = cuda_ok(cudaEventRecord(c.evDrawDone, c.stream()), "event record");
+	ok = ok && cuda_ok(cudaStreamWaitEvent(c.readStream, c.evDrawDone, 0), "stream wait");
+	ok = ok && cuda_ok(cudaMemcpyAsync(dst, fb->image, need, cudaMemcpyDeviceToHost, c.readStream), "framebuffer read");
+	ok = ok && cuda_ok(cudaEventRecord(c.evReadDone, c.readStream), "event record");
+	fb->readPending = true; /* the next draw into this framebuffer waits for the copy (DN_draw) */
+	return ok;
+}
+
+extern "C" bool DN_b200_wait_framebuffer(void)
+{
+	return cuda_ok(cudaStreamSynchronize(ctx().readStream), "framebuffer read");
+}
+
 extern "C" bool DN_b200_clear_framebuffer(GLuint id, float value)
 {
 	Framebuffer* fb = find_fb(id);
@@ -845,6 +875,12 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_draw: cubemap skies are not supported by the CUDA back end; using the sky gradient");
 
 	cudaStream_t s = ctx().stream();
+	if(fb->readPending)
+	{
+		/* pixels of the previous frame may still be on their way to the host */
+		cuda_ok(cudaStreamWaitEvent(s, ctx().evReadDone, 0), "stream wait");
+		fb->readPending = false;
+	}
 	ScopedTimer timer(&v->stats.lastDrawMs, s);
 
 	/* materials travel with every draw, as upstream (voxel.c:823-824) */

@@ -27,6 +27,7 @@ struct Framebuffer
 	int     width = 0, height = 0;
 	float4* image = nullptr;
 	DnbHit* hits = nullptr;
+	bool    readPending = false; /* an asynchronous read-back of this image has been queued */
 };
 
 struct Context
@@ -35,6 +36,8 @@ struct Context
 	int          device = 0;
 	cudaStream_t ownStream = nullptr;    /* kernels */
 	cudaStream_t uploadStream = nullptr; /* host->device copies of edited chunks + their scatter */
+	cudaStream_t readStream = nullptr;   /* asynchronous framebuffer read-back */
+	cudaEvent_t  evDrawDone = nullptr, evReadDone = nullptr;
 	cudaStream_t userStream = nullptr;   /* DN_b200_set_stream */
 	bool         useUserStream = false;
 	cudaEvent_t  evUploadDone = nullptr, evComputeDone = nullptr;
@@ -63,6 +66,7 @@ struct VolumeImpl
 	std::vector<uint32_t> slotNumVoxels;  /* per slot: records in use */
 	std::vector<uint32_t> freeNodes[NUM_NODE_CLASSES];
 	size_t                recordTop = 0;  /* bump pointer of the record pool */
+	size_t                residentGroups = 0; /* sum over resident chunks of ceil(records/32): upper bound of the request count */
 
 	/* ---- edit tracking ---- */
 	std::vector<uint32_t> touched;        /* tiles to reconcile at the next writing sync */

@@ -539,6 +539,7 @@ extern "C" bool DN_set_map_size(DNvolume* vol, DNuvec3 size)
 	for(int c = 0; c < NUM_NODE_CLASSES; c++)
 		v->freeNodes[c].clear();
 	v->recordTop = 0;
+	v->residentGroups = 0;
 	for(int a = 0; a < 3; a++)
 	{
 		v->occMin[a] = 0x3FFFFFFF;

@@ -33,6 +33,9 @@ bool   DN_b200_framebuffer_size(GLuint fb, int* width, int* height);
 void*  DN_b200_framebuffer_device_ptr(GLuint fb);                     /* float4[width*height] in device memory */
 bool   DN_b200_read_framebuffer(GLuint fb, float* dst, size_t bytes); /* synchronous device -> host copy */
 bool   DN_b200_clear_framebuffer(GLuint fb, float value);
+/* asynchronous read-back on a side stream: ordered after the work queued so far, overlaps with what is queued next */
+bool   DN_b200_read_framebuffer_async(GLuint fb, float* dst, size_t bytes);
+bool   DN_b200_wait_framebuffer(void);
 
 /* per-pixel first-hit capture for parity tests: status 0 box miss / 1 no hit / 2 hit, tile, voxel, record-in-chunk */
 typedef struct DNb200hit { int32_t status; uint32_t mapIndex, localIndex, recordIndex; } DNb200hit;
