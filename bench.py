@@ -73,9 +73,10 @@ class ClockSampler(threading.Thread):
     """SM clock and throttle reasons during the timed region, sampled through NVML every 5 ms (the quantities of the
     nvidia-smi line in B200_PROFILING.md; nvidia-smi's own loop is too coarse for a region of tens of milliseconds)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.005):
         super().__init__(daemon=True)
         self.index = index
+        self.period_s = period_s
         self.samples = []
         self.reasons = set()
         self.sm_max = None
@@ -102,7 +103,7 @@ class ClockSampler(threading.Thread):
                     self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
                 except Exception:
                     pass
-                time.sleep(0.005)
+                time.sleep(self.period_s)
         except Exception as ex:  # NVML missing: report no clocks rather than fail the benchmark
             self.error = repr(ex)
 
@@ -256,16 +257,24 @@ def run_ours(args, scene, tiles, res, desc):
     e.synchronize()
     t_build = time.perf_counter() - t_build
     from doonengine_b200.multigpu import ShardedEngine
-    sh = ShardedEngine(e, rank, world, torch, dist, device)  # N = 1: plain DN_draw / light phases, no collectives
+    # N = 1: plain DN_draw / light phases.  N > 1: replicas attached over peer memory (NVLink): the kernels exchange pixels and
+    # staged words themselves, a device-side barrier separates the phases; no collective on the frame path.
+    sh = ShardedEngine(e, rank, world, torch, dist, device, exchange=args.exchange)
 
-    fb = e.framebuffer(w, h)
+    # three framebuffers in rotation: the read-back of frame k (side stream) overlaps frame k+1, and no replica draws
+    # into an image the root is still copying out
+    fbs = [L.DN_b200_create_framebuffer(w, h) for _ in range(3)]
+    if not all(fbs):
+        raise SystemExit("DN_b200_create_framebuffer failed")
+    for f in fbs:
+        L.DN_b200_clear_framebuffer(f, 0.0)
+    e.synchronize()
+    for f in fbs:
+        sh.mirror_framebuffer(f, root=0)
     fb_bytes = w * h * 16
-    host_image = torch.empty(fb_bytes, dtype=torch.uint8, pin_memory=True)
+    host_images = [torch.empty(fb_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(3)] if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
     view, proj = e.view_projection(h / w)
-    words = (e.num_tiles() + 31) // 32
-    group_rows = h // 16
-    band_rows = (group_rows + world - 1) // world  # 16-pixel rows per rank
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -273,12 +282,14 @@ def run_ours(args, scene, tiles, res, desc):
     def step(k, timed, read_back):
         """one frame; returns the events bracketing its phases."""
         marks = [ev() for _ in range(6)] if timed else None
+        fb = fbs[k % 3]
+        read_back = read_back and rank == 0  # the whole image is assembled on the root (mirrored pixel stores)
         if timed:
             marks[0].record(stream)
         sh.draw(fb, view, proj)
         if read_back:
-            # the copy to pinned host memory runs on a side stream, overlapped with compaction and lighting
-            L.DN_b200_read_framebuffer_async(fb, host_image.data_ptr(), fb_bytes)
+            # the copy to pinned host memory runs on a side stream, overlapped with compaction, lighting and the next draw
+            L.DN_b200_read_framebuffer_async(fb, host_images[k % 3].data_ptr(), fb_bytes)
         if timed:
             marks[1].record(stream)
         L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
@@ -292,7 +303,7 @@ def run_ours(args, scene, tiles, res, desc):
         if timed:
             marks[4].record(stream)
         if read_back:
-            L.DN_b200_wait_framebuffer()
+            L.DN_b200_wait_framebuffer_read(fbs[(k - 1) % 3])  # frame k-1's pixels are on the host
         if timed:
             marks[5].record(stream)
         return marks, int(e.vol.contents.numLightingRequests)
@@ -306,8 +317,9 @@ def run_ours(args, scene, tiles, res, desc):
         """K timed steps, L2 flushed (untimed) between them; returns per-phase ms sums, voxels lit, requests."""
         lit0 = e.stats()["voxelsLit"]
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler = ClockSampler(local, args.sampler_ms / 1000.0)
+        if args.sampler_ms > 0:
+            sampler.start()
         all_marks, reqs = [], 0
         wall0 = time.perf_counter()
         for i in range(steps):
@@ -315,13 +327,19 @@ def run_ours(args, scene, tiles, res, desc):
             m, r = step(k0 + i, True, read_back)
             all_marks.append(m)
             reqs += r
+        drain0, drain1 = ev(), ev()
+        drain0.record(stream)
+        if read_back and rank == 0:
+            L.DN_b200_wait_framebuffer()  # the last frame's pixels
+        drain1.record(stream)
         barrier()
         wall = time.perf_counter() - wall0
-        clocks = sampler.finish()
+        clocks = sampler.finish() if args.sampler_ms > 0 else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         phases = np.zeros(5)
         for m in all_marks:
             for j in range(5):
                 phases[j] += m[j].elapsed_time(m[j + 1])
+        phases[4] += drain0.elapsed_time(drain1)
         lit = e.stats()["voxelsLit"] - lit0
         return phases, lit, reqs, clocks, wall
 
@@ -357,10 +375,10 @@ def run_ours(args, scene, tiles, res, desc):
     if rank == 0:
         e.enable_counters(True)
         e.counters(reset=True)
-        sh.draw(fb, view, proj)
-        cd = e.counters(reset=True)  # N > 1: rank 0's band only; the draw roofline is reported for N = 1
+        sh.draw(fbs[0], view, proj)
+        cd = e.counters(reset=True)  # N > 1: rank 0's rows only; the draw roofline is reported for N = 1
     else:
-        sh.draw(fb, view, proj)
+        sh.draw(fbs[0], view, proj)
     L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
     r_count = int(e.vol.contents.numLightingRequests)
     sh.light_compute(1, 1000, frame_time(args.warmup + 2 * args.steps))
@@ -398,20 +416,30 @@ def run_ours(args, scene, tiles, res, desc):
 
     if rank == 0:
         stats = e.stats()
-        launches_per_step = 7  # draw, compaction count + scan + write, lighting, commit, visible merge
+        # draw, compaction count + scan + write, lighting, commit, visible merge; peer mode adds 2 barriers + the visible-bitmap merge,
+        # collective mode one OR kernel per rank and bitmap
+        launches_per_step = 7 if world == 1 else (10 if sh.exchange == "peer" else 7 + 2 * world)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "parallelism": "map replicated, request list and screen rows sharded x%d" % world,
+            "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "parallelism": ("map replicated, request CTAs and 16-pixel rows interleaved x%d, exchange=%s" % (world, sh.exchange)) if world > 1 else "1 GPU",
                        "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
                        "resident_records": int(stats["residentRecords"]), "requests_per_step": reqs / K, "voxels_lit_per_step": lit / K, "build_s": t_build},
             "frame_ms": {"draw": draw_ms, "sync_compact": sync_ms, "light_kernel": light_ms, "commit": commit_ms, "frame": frame_ms, "frame_with_readback": frame2_ms,
                          "wall_per_step_incl_flush": 1000.0 * wall / K},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8192 + 2416, "d2h_bytes_per_step": fb_bytes + 4, "ms_per_step": frame2_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8192 + 2416, "d2h_bytes_per_step": fb_bytes + 4, "ms_per_step": frame2_ms,
+                    "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps frame k+1; the last copy is drained inside the timed region)"},
             "gpu_launches": launches_per_step * args.steps * 2,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)
+    if world > 1:
+        ep, to = sh.barrier_status() if sh.exchange == "peer" else (0, 0)
+        if to:
+            print("rank %d: %d device-barrier time-outs -- results invalid" % (rank, to), file=sys.stderr, flush=True)
+    sh.close()
+    for f in fbs:
+        L.DN_b200_delete_framebuffer(f)
     e.close()
     if world > 1:
         dist.destroy_process_group()
@@ -425,6 +453,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "collective"], help="N > 1: kernels exchange over peer memory (default) or host-driven NCCL all-gathers")
+    ap.add_argument("--sampler-ms", type=float, default=20.0, help="NVML clock sampling period during the timed region (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

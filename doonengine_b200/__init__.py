@@ -85,6 +85,14 @@ class DNb200stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class DNb200peerBuffers(C.Structure):
+    """where one replica's exchange buffers are mapped in this process (include/DoonEngine/b200.h)."""
+    _fields_ = [("staging", C.c_void_p), ("mailbox", C.c_void_p), ("visible", C.c_void_p), ("propagate", C.c_void_p),
+                ("stagingRequestCap", C.c_uint64)]
+
+
+PEER_AUTO, PEER_MANUAL = 0, 1
+
 assert C.sizeof(DNvolume) == 232 and C.sizeof(DNvoxel) == 20 and C.sizeof(DNmat4) == 64
 
 MESSAGE_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_char_p)
@@ -153,6 +161,7 @@ _PROTOTYPES = {
     "DN_b200_clear_framebuffer": (C.c_bool, [C.c_uint32, C.c_float]),
     "DN_b200_read_framebuffer_async": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
     "DN_b200_wait_framebuffer": (C.c_bool, []),
+    "DN_b200_wait_framebuffer_read": (C.c_bool, [C.c_uint32]),
     "DN_b200_capture_hits": (C.c_bool, [C.c_uint32, C.c_bool]),
     "DN_b200_read_hits": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
     "DN_b200_fetch_lighting_requests": (C.c_size_t, [C.POINTER(DNvolume)]),
@@ -170,6 +179,16 @@ _PROTOTYPES = {
     "DN_b200_light_commit": (C.c_bool, [C.POINTER(DNvolume)]),
     "DN_b200_staging_slice_bytes": (C.c_size_t, [C.POINTER(DNvolume)]),
     "DN_b200_or_bitmap": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_void_p]),
+    "DN_b200_peer_prepare": (C.c_bool, [C.POINTER(DNvolume), C.c_size_t, C.POINTER(DNb200peerBuffers)]),
+    "DN_b200_ipc_export": (C.c_bool, [C.c_void_p, C.c_void_p]),
+    "DN_b200_ipc_open": (C.c_void_p, [C.c_void_p]),
+    "DN_b200_ipc_close": (C.c_bool, [C.c_void_p]),
+    "DN_b200_peer_attach": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int, C.POINTER(DNb200peerBuffers), C.c_int]),
+    "DN_b200_peer_detach": (None, [C.POINTER(DNvolume)]),
+    "DN_b200_peer_capacity_ok": (C.c_bool, [C.POINTER(DNvolume)]),
+    "DN_b200_framebuffer_set_mirror": (C.c_bool, [C.c_uint32, C.c_void_p]),
+    "DN_b200_peer_exchange_visible": (C.c_bool, [C.POINTER(DNvolume)]),
+    "DN_b200_peer_barrier_status": (C.c_bool, [C.POINTER(DNvolume), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
 }
 
 _lib = None

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdoon_b200.so")
 
-SOURCES = ["draw.cu", "light.cu", "compact.cu", "upload.cu", "engine.cpp", "volume_host.cpp"]
+SOURCES = ["draw.cu", "light.cu", "compact.cu", "upload.cu", "peer.cu", "engine.cpp", "volume_host.cpp"]
 HEADERS = ["layout.h", "kernels.h", "engine.h", "hostmath.h", "vecmath.cuh", "trace.cuh"]
 PUBLIC_HEADERS = ["DoonEngine/voxel.h", "DoonEngine/b200.h", "DoonEngine/globals.h", "DoonEngine/mathtypes.h"]
 

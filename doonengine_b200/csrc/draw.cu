@@ -68,13 +68,15 @@ DNB_FN f3 voxel_color(const DnbScene& S, uint32_t viewMode, uint4 rec, f3 colorA
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256) dn_draw_kernel(DnbScene S, DnbDrawParams P, float4* __restrict__ image, DnbHit* __restrict__ hits)
+__global__ void __launch_bounds__(256) dn_draw_kernel(DnbScene S, DnbDrawParams P, float4* __restrict__ image, float4* __restrict__ mirror, DnbHit* __restrict__ hits)
 {
-	/* 32x8 pixel CTA made of 4x2 warp footprints of 8x4 pixels */
+	/* 32x8 pixel CTA made of 4x2 warp footprints of 8x4 pixels; blockIdx.y counts 8-row strips of the 16-pixel group rows
+	 * rowBegin, rowBegin + rowStride, ... this launch owns */
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-	const int py = P.rowBegin * 16 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-	if(px >= (P.width / 16) * 16 || py >= P.rowEnd * 16)
+	const int groupRow = P.rowBegin + (int)(blockIdx.y >> 1) * P.rowStride;
+	const int py = groupRow * 16 + (int)(blockIdx.y & 1u) * 8 + (warp >> 2) * 4 + (lane >> 3);
+	if(px >= (P.width / 16) * 16 || groupRow >= P.rowEnd)
 		return;
 
 	RayState st;
@@ -159,7 +161,10 @@ __global__ void __launch_bounds__(256) dn_draw_kernel(DnbScene S, DnbDrawParams 
 	finalColor = mk3(powf(finalColor.x, 0.4545f), powf(finalColor.y, 0.4545f), powf(finalColor.z, 0.4545f));
 
 	const size_t at = (size_t)py * (size_t)P.width + (size_t)px;
-	image[at] = make_float4(finalColor.x, finalColor.y, finalColor.z, finalDepth);
+	const float4 pixel = make_float4(finalColor.x, finalColor.y, finalColor.z, finalDepth);
+	image[at] = pixel;
+	if(mirror)
+		mirror[at] = pixel; /* the root replica's framebuffer in peer memory: the gather is fused into the draw */
 	if(hits)
 		hits[at] = hit;
 
@@ -175,16 +180,19 @@ __global__ void __launch_bounds__(256) dn_draw_kernel(DnbScene S, DnbDrawParams 
 	}
 }
 
-extern "C" cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, DnbHit* hits, cudaStream_t stream)
+extern "C" cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, float4* mirror, DnbHit* hits, cudaStream_t stream)
 {
 	const int cols = (params->width / 16) * 16;
-	const int rows = (params->rowEnd - params->rowBegin) * 16;
-	if(cols <= 0 || rows <= 0)
+	const int stride = params->rowStride > 0 ? params->rowStride : 1;
+	const int groups = params->rowEnd > params->rowBegin ? (params->rowEnd - params->rowBegin + stride - 1) / stride : 0;
+	if(cols <= 0 || groups <= 0)
 		return cudaSuccess;
-	dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 7) / 8));
+	DnbDrawParams p = *params;
+	p.rowStride = stride;
+	dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(groups * 2));
 	if(scene->counters)
-		dn_draw_kernel<true><<<grid, 256, 0, stream>>>(*scene, *params, image, hits);
+		dn_draw_kernel<true><<<grid, 256, 0, stream>>>(*scene, p, image, mirror, hits);
 	else
-		dn_draw_kernel<false><<<grid, 256, 0, stream>>>(*scene, *params, image, hits);
+		dn_draw_kernel<false><<<grid, 256, 0, stream>>>(*scene, p, image, mirror, hits);
 	return cudaGetLastError();
 }

@@ -31,6 +31,15 @@ bool cuda_ok(cudaError_t e, const char* what)
 	return false;
 }
 
+static bool peer_barrier(VolumeImpl* v);
+
+/* requests per replica in the host-driven (all-gather) sharding: ceil(total / world) rounded up to whole 4-request CTAs */
+static inline size_t slice_len(size_t total, int world)
+{
+	const size_t per = (total + (size_t)world - 1) / (size_t)world;
+	return (per + 3) & ~(size_t)3;
+}
+
 template <typename T> void device_free(DeviceArray<T>& a)
 {
 	if(a.ptr)
@@ -122,6 +131,8 @@ void device_destroy(VolumeImpl* v)
 	device_free(v->tileSlot); device_free(v->occ64); device_free(v->visible); device_free(v->propagate); device_free(v->forced);
 	device_free(v->slots); device_free(v->records); device_free(v->materials); device_free(v->requests); device_free(v->staging);
 	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->blob); device_free(v->litCounter);
+	device_free(v->mailbox); device_free(v->barrierStatus);
+	v->peerAttached = false;
 	if(v->pinnedBlob) cudaFreeHost(v->pinnedBlob);
 	if(v->pinnedScalars) cudaFreeHost(v->pinnedScalars);
 	if(v->counters) cudaFree(v->counters);
@@ -436,8 +447,11 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 		vol->voxelCap = v->records.cap;
 	}
 
-	/* the scatter must not overtake kernels that still read the old chunk contents */
+	/* the scatter must not overtake kernels that still read the old chunk contents -- on this GPU, or (sharded over peer
+	 * memory) the peers' merge kernels, which read this replica's visible bitmap that the scatter is about to edit */
 	cudaStream_t cs = c.stream();
+	if(v->peerAttached && v->peerMode == DN_B200_PEER_AUTO && v->peerMergeUnfenced)
+		peer_barrier(v);
 	cuda_ok(cudaEventRecord(c.evComputeDone, cs), "event record");
 	cuda_ok(cudaStreamWaitEvent(c.uploadStream, c.evComputeDone, 0), "stream wait");
 
@@ -659,6 +673,7 @@ extern "C" void DN_quit(void)
 	{
 		if(fb.image) cudaFree(fb.image);
 		if(fb.hits) cudaFree(fb.hits);
+		if(fb.evRead) cudaEventDestroy(fb.evRead);
 	}
 	c.framebuffers.clear();
 	cudaEventDestroy(c.evUploadDone); cudaEventDestroy(c.evComputeDone); cudaEventDestroy(c.evT0); cudaEventDestroy(c.evT1);
@@ -729,8 +744,10 @@ extern "C" void DN_b200_delete_framebuffer(GLuint id)
 	if(!fb)
 		return;
 	cudaStreamSynchronize(ctx().stream());
+	cudaStreamSynchronize(ctx().readStream);
 	cudaFree(fb->image);
 	if(fb->hits) cudaFree(fb->hits);
+	if(fb->evRead) cudaEventDestroy(fb->evRead);
 	*fb = Framebuffer();
 }
 
@@ -774,6 +791,9 @@ extern "C" bool DN_b200_read_framebuffer_async(GLuint id, float* dst, size_t byt
 	ok = ok && cuda_ok(cudaStreamWaitEvent(c.readStream, c.evDrawDone, 0), "stream wait");
 	ok = ok && cuda_ok(cudaMemcpyAsync(dst, fb->image, need, cudaMemcpyDeviceToHost, c.readStream), "framebuffer read");
 	ok = ok && cuda_ok(cudaEventRecord(c.evReadDone, c.readStream), "event record");
+	if(ok && !fb->evRead)
+		ok = cuda_ok(cudaEventCreateWithFlags(&fb->evRead, cudaEventDisableTiming), "event create");
+	ok = ok && cuda_ok(cudaEventRecord(fb->evRead, c.readStream), "event record");
 	fb->readPending = true; /* the next draw into this framebuffer waits for the copy (DN_draw) */
 	return ok;
 }
@@ -781,6 +801,18 @@ extern "C" bool DN_b200_read_framebuffer_async(GLuint id, float* dst, size_t byt
 extern "C" bool DN_b200_wait_framebuffer(void)
 {
 	return cuda_ok(cudaStreamSynchronize(ctx().readStream), "framebuffer read");
+}
+
+/* waits for the last asynchronous read-back of ONE framebuffer (the copies of other framebuffers keep flying): with two or
+ * three framebuffers in rotation the copy of frame k overlaps the whole of frame k+1 */
+extern "C" bool DN_b200_wait_framebuffer_read(GLuint id)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb)
+		return false;
+	if(!fb->evRead)
+		return true;
+	return cuda_ok(cudaEventSynchronize(fb->evRead), "framebuffer read");
 }
 
 extern "C" bool DN_b200_clear_framebuffer(GLuint id, float value)
@@ -878,7 +910,7 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 	if(fb->readPending)
 	{
 		/* pixels of the previous frame may still be on their way to the host */
-		cuda_ok(cudaStreamWaitEvent(s, ctx().evReadDone, 0), "stream wait");
+		cuda_ok(cudaStreamWaitEvent(s, fb->evRead ? fb->evRead : ctx().evReadDone, 0), "stream wait");
 		fb->readPending = false;
 	}
 	ScopedTimer timer(&v->stats.lastDrawMs, s);
@@ -904,7 +936,15 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 	dp.width = fb->width;
 	dp.height = fb->height;
 	const int groupRows = fb->height / 16;
-	if(v->shardWorld > 1)
+	dp.rowStride = 1;
+	if(v->peerAttached)
+	{
+		/* interleaved group rows: rank, rank + world, ... */
+		dp.rowBegin = v->shardRank;
+		dp.rowEnd = groupRows;
+		dp.rowStride = v->shardWorld;
+	}
+	else if(v->shardWorld > 1)
 	{
 		const int per = (groupRows + v->shardWorld - 1) / v->shardWorld;
 		dp.rowBegin = std::min(groupRows, per * v->shardRank);
@@ -915,7 +955,16 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 		dp.rowBegin = 0;
 		dp.rowEnd = groupRows;
 	}
-	cuda_ok(dnb_launch_draw(&scene, &dp, fb->image, fb->hits, s), "draw kernel");
+	cuda_ok(dnb_launch_draw(&scene, &dp, fb->image, v->peerAttached ? fb->mirror : nullptr, fb->hits, s), "draw kernel");
+
+	/* sharded over peer memory: once every replica has drawn (and its mirrored pixels have landed), OR the peers' visible
+	 * bits into this replica's, so that every replica compacts the identical request list */
+	if(v->peerAttached && v->peerMode == DN_B200_PEER_AUTO)
+	{
+		peer_barrier(v);
+		cuda_ok(dnb_launch_peer_or_visible(&v->peers, v->visible.ptr, (uint32_t)((num_tiles(vol) + 31) / 32), s), "visible merge");
+		v->peerMergeUnfenced = true;
+	}
 }
 
 static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSamples, float time)
@@ -931,8 +980,8 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 
 	const size_t total = v->requestsValid;
 	v->stagedRequests = total;
-	if(total == 0)
-		return true;
+	if(total == 0 && !v->peerAttached)
+		return true; /* (attached replicas still fence and clear their propagate bitmap below) */
 
 	if(numDiffuseSamples < 0) numDiffuseSamples = 0;
 	if(numDiffuseSamples > DNB_MAX_SAMPLES || vol->diffuseBounceLimit > DNB_MAX_BOUNCES)
@@ -971,22 +1020,58 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	DnbScene scene;
 	fill_scene(v, &scene);
 
-	/* slice of the request list this process lights */
-	size_t first = 0, count = total, paddedTotal = total;
-	if(v->shardWorld > 1)
+	/* the CTAs (4 requests each) this process lights, and where their staged words go */
+	const uint32_t totalCtas = (uint32_t)((total + 3) / 4);
+	uint32_t firstCta = 0, ctaStride = 1, numCtas = totalCtas;
+	DnbStagingTargets targets;
+	memset(&targets, 0, sizeof(targets));
+	if(v->peerAttached)
 	{
-		const size_t per = (total + v->shardWorld - 1) / v->shardWorld;
-		first = std::min(total, per * (size_t)v->shardRank);
-		count = std::min(total, per * (size_t)(v->shardRank + 1)) - first;
-		paddedTotal = per * (size_t)v->shardWorld;
+		if(total > v->peerRequestCap)
+		{
+			report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "DN_update_lighting: %zu lighting requests exceed the %zu the attached peer staging arrays hold; detach, DN_b200_peer_prepare with a larger capacity and attach again",
+			       total, v->peerRequestCap);
+			v->stagedRequests = 0;
+			return false;
+		}
+		/* interleaved: rank, rank + world, ...; every replica's staging array is a target (stores over NVLink) */
+		firstCta = (uint32_t)v->shardRank;
+		ctaStride = (uint32_t)v->shardWorld;
+		numCtas = totalCtas > firstCta ? (totalCtas - firstCta + ctaStride - 1) / ctaStride : 0;
+		targets.count = v->peers.world;
+		for(uint32_t p = 0; p < v->peers.world; p++)
+			targets.dst[p] = v->peers.staging[p];
+		/* the peers' previous commit read this replica's staging and propagate arrays: make sure they are done with them */
+		if(v->peerMode == DN_B200_PEER_AUTO && !v->peerFenceSinceCommit)
+			peer_barrier(v);
+		const size_t words = (num_tiles(vol) + 31) / 32;
+		cuda_ok(cudaMemsetAsync(v->propagate.ptr, 0, words * sizeof(uint32_t), s), "propagate bitmap clear");
 	}
-	if(!device_reserve(v->staging, paddedTotal * 96, false, false, "lighting staging"))
-		return false;
+	else
+	{
+		size_t paddedTotal = total;
+		if(v->shardWorld > 1)
+		{
+			/* contiguous slice [rank * per, (rank + 1) * per): the unit of the host-driven all-gather */
+			const size_t per = slice_len(total, v->shardWorld);
+			const size_t first = std::min(total, per * (size_t)v->shardRank);
+			const size_t count = std::min(total, per * (size_t)(v->shardRank + 1)) - first;
+			paddedTotal = per * (size_t)v->shardWorld;
+			firstCta = (uint32_t)(first / 4);
+			numCtas = (uint32_t)((count + 3) / 4);
+		}
+		if(!device_reserve(v->staging, paddedTotal * 96, false, false, "lighting staging"))
+			return false;
+		targets.count = 1;
+		targets.dst[0] = v->staging.ptr;
+	}
 
 	ScopedTimer timer(&v->stats.lastLightMs, s);
 	bool ok = cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
-	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, (uint32_t)first, (uint32_t)count, v->staging.ptr, s), "lighting kernel");
+	/* a slice that is not the last one ends on a CTA boundary (slice_len is a multiple of 4); the last CTA of the list is cut by numRequests */
+	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
+	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, s), "lighting kernel");
 	return ok;
 }
 
@@ -998,14 +1083,19 @@ static bool light_commit(VolumeImpl* v)
 	DnbScene scene;
 	fill_scene(v, &scene);
 	ScopedTimer timer(&v->stats.lastCommitMs, s);
-	return cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, (uint32_t)v->stagedRequests, v->staging.ptr, v->litCounter.ptr, s), "commit kernel");
+	if(v->peerAttached && v->peerMode == DN_B200_PEER_AUTO)
+		peer_barrier(v); /* every replica has stored its staged words into this replica's staging array */
+	const bool ok = cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, (uint32_t)v->stagedRequests, v->staging.ptr, v->litCounter.ptr,
+	                                          v->peerAttached ? &v->peers : nullptr, s), "commit kernel");
+	v->peerFenceSinceCommit = false;
+	return ok;
 }
 
 extern "C" void DN_update_lighting(DNvolume* vol, int numDiffuseSamples, int maxDiffuseSamples, float time)
 {
 	VolumeImpl* v = impl_of(vol);
-	if(v->shardWorld > 1)
-		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_update_lighting on a sharded volume lights only this rank's slice; use DN_b200_light_compute + all-gather + DN_b200_light_commit");
+	if(v->shardWorld > 1 && !(v->peerAttached && v->peerMode == DN_B200_PEER_AUTO))
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_update_lighting on a sharded volume lights only this rank's slice; use DN_b200_light_compute + exchange + DN_b200_light_commit");
 	if(light_compute(v, numDiffuseSamples, maxDiffuseSamples, time))
 		light_commit(v);
 }
@@ -1023,8 +1113,7 @@ extern "C" bool DN_b200_light_commit(DNvolume* vol)
 extern "C" size_t DN_b200_staging_slice_bytes(DNvolume* vol)
 {
 	VolumeImpl* v = impl_of(vol);
-	const size_t per = (v->stagedRequests + v->shardWorld - 1) / v->shardWorld;
-	return per * 96 * sizeof(uint32_t);
+	return slice_len(v->stagedRequests, v->shardWorld) * 96 * sizeof(uint32_t);
 }
 
 extern "C" bool DN_b200_set_shard(DNvolume* vol, int rank, int worldSize)
@@ -1077,9 +1166,8 @@ static bool array_info(VolumeImpl* v, DNb200array which, void** ptr, size_t* byt
 	case DN_B200_PROPAGATE:  *ptr = v->propagate.ptr; *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
 	case DN_B200_STAGING:
 	{
-		const size_t per = (v->stagedRequests + v->shardWorld - 1) / v->shardWorld;
 		*ptr = v->staging.ptr;
-		*bytes = per * v->shardWorld * 96 * sizeof(uint32_t);
+		*bytes = (v->peerAttached ? v->stagedRequests : slice_len(v->stagedRequests, v->shardWorld) * v->shardWorld) * 96 * sizeof(uint32_t);
 		return true;
 	}
 	}
@@ -1192,4 +1280,170 @@ extern "C" bool DN_b200_or_bitmap(DNvolume* vol, DNb200array which, const void* 
 	const uint32_t words = (uint32_t)((num_tiles(vol) + 31) / 32);
 	uint32_t* dst = which == DN_B200_VISIBLE ? v->visible.ptr : v->propagate.ptr;
 	return cuda_ok(dnb_launch_or_bits(dst, (const uint32_t*)deviceBitmap, words, ctx().stream()), "bitmap merge");
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* multi-GPU over peer memory (DoonEngine/b200.h)                                                     */
+
+namespace dnb
+{
+/* queues one device-side barrier over all replicas on the compute stream (peer.cu) */
+static bool peer_barrier(VolumeImpl* v)
+{
+	v->peerEpoch++;
+	v->peerFenceSinceCommit = true;
+	v->peerMergeUnfenced = false;
+	return cuda_ok(dnb_launch_peer_barrier(&v->peers, v->peerEpoch, v->barrierStatus.ptr, ctx().stream()), "peer barrier");
+}
+} // namespace dnb
+
+extern "C" bool DN_b200_peer_prepare(DNvolume* vol, size_t requestCap, DNb200peerBuffers* mine)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_b200_peer_prepare") || !mine)
+		return false;
+	if(v->peerAttached)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_peer_prepare: detach first");
+		return false;
+	}
+	if(requestCap == 0)
+		requestCap = v->residentGroups + v->residentGroups / 4 + 4096;
+	if(!device_reserve(v->staging, requestCap * 96, false, false, "lighting staging"))
+		return false;
+	/* the mailbox is allocated once and never reset: epochs keep counting across re-attachments */
+	if(!v->mailbox.ptr && !device_reserve(v->mailbox, 32, false, true, "peer mailbox"))
+		return false;
+	if(!v->barrierStatus.ptr && !device_reserve(v->barrierStatus, 2, false, true, "peer barrier status"))
+		return false;
+	if(!DN_b200_synchronize())
+		return false;
+	mine->staging = v->staging.ptr;
+	mine->mailbox = v->mailbox.ptr;
+	mine->visible = v->visible.ptr;
+	mine->propagate = v->propagate.ptr;
+	mine->stagingRequestCap = v->staging.cap / 96;
+	return true;
+}
+
+extern "C" bool DN_b200_ipc_export(const void* devicePtr, void* handle64)
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 opaque bytes");
+	cudaIpcMemHandle_t h;
+	if(!cuda_ok(cudaIpcGetMemHandle(&h, const_cast<void*>(devicePtr)), "cudaIpcGetMemHandle"))
+		return false;
+	memcpy(handle64, &h, 64);
+	return true;
+}
+
+extern "C" void* DN_b200_ipc_open(const void* handle64)
+{
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	void* p = nullptr;
+	if(!cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"))
+		return nullptr;
+	return p;
+}
+
+extern "C" bool DN_b200_ipc_close(void* devicePtr)
+{
+	return cuda_ok(cudaIpcCloseMemHandle(devicePtr), "cudaIpcCloseMemHandle");
+}
+
+extern "C" bool DN_b200_peer_attach(DNvolume* vol, int rank, int worldSize, const DNb200peerBuffers* peers, DNb200peerMode mode)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_b200_peer_attach"))
+		return false;
+	if(worldSize < 1 || worldSize > DNB_MAX_PEERS || rank < 0 || rank >= worldSize || !peers)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_peer_attach: bad rank %d / world %d (at most %d replicas)", rank, worldSize, DNB_MAX_PEERS);
+		return false;
+	}
+	if(peers[rank].staging != v->staging.ptr || peers[rank].mailbox != v->mailbox.ptr || !v->mailbox.ptr)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_peer_attach: entry %d must be this replica's own buffers (DN_b200_peer_prepare)", rank);
+		return false;
+	}
+	DN_b200_synchronize();
+	memset(&v->peers, 0, sizeof(v->peers));
+	v->peers.world = (uint32_t)worldSize;
+	v->peers.rank = (uint32_t)rank;
+	size_t cap = (size_t)-1;
+	for(int p = 0; p < worldSize; p++)
+	{
+		if(!peers[p].staging || !peers[p].mailbox || !peers[p].visible || !peers[p].propagate)
+		{
+			report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_peer_attach: replica %d has unmapped buffers", p);
+			return false;
+		}
+		v->peers.staging[p] = (uint32_t*)peers[p].staging;
+		v->peers.mailbox[p] = (uint32_t*)peers[p].mailbox;
+		v->peers.visible[p] = (const uint32_t*)peers[p].visible;
+		v->peers.propagate[p] = (const uint32_t*)peers[p].propagate;
+		cap = std::min<size_t>(cap, (size_t)peers[p].stagingRequestCap);
+	}
+	v->peerRequestCap = cap;
+	v->peerMode = (int)mode;
+	v->shardRank = rank;
+	v->shardWorld = worldSize;
+	v->peerFenceSinceCommit = false;
+	v->peerMergeUnfenced = false;
+	v->peerAttached = true;
+	return true;
+}
+
+extern "C" void DN_b200_peer_detach(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!v->peerAttached)
+		return;
+	if(ctx().ready)
+		DN_b200_synchronize();
+	v->peerAttached = false;
+	v->shardRank = 0;
+	v->shardWorld = 1;
+}
+
+extern "C" bool DN_b200_peer_capacity_ok(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	return !v->peerAttached || v->requestsValid <= v->peerRequestCap;
+}
+
+extern "C" bool DN_b200_framebuffer_set_mirror(GLuint id, void* mirrorImage)
+{
+	Framebuffer* fb = find_fb(id);
+	if(!fb)
+		return false;
+	cudaStreamSynchronize(ctx().stream());
+	fb->mirror = (float4*)mirrorImage;
+	return true;
+}
+
+extern "C" bool DN_b200_peer_exchange_visible(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_b200_peer_exchange_visible") || !v->peerAttached)
+		return false;
+	return cuda_ok(dnb_launch_peer_or_visible(&v->peers, v->visible.ptr, (uint32_t)((num_tiles(vol) + 31) / 32), ctx().stream()), "visible merge");
+}
+
+extern "C" bool DN_b200_peer_barrier_status(DNvolume* vol, uint64_t* epochs, uint32_t* timeouts)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!v->barrierStatus.ptr || !DN_b200_synchronize())
+		return false;
+	uint32_t st[2] = {0, 0};
+	if(!cuda_ok(cudaMemcpy(st, v->barrierStatus.ptr, sizeof(st), cudaMemcpyDeviceToHost), "barrier status read"))
+		return false;
+	if(epochs) *epochs = st[0];
+	if(timeouts) *timeouts = st[1];
+	if(st[1] > v->peerTimeoutsReported)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "peer barrier timed out %u time(s): a replica did not arrive; results after that point are undefined", st[1] - v->peerTimeoutsReported);
+		v->peerTimeoutsReported = st[1];
+	}
+	return true;
 }

@@ -28,6 +28,8 @@ struct Framebuffer
 	float4* image = nullptr;
 	DnbHit* hits = nullptr;
 	bool    readPending = false; /* an asynchronous read-back of this image has been queued */
+	cudaEvent_t evRead = nullptr; /* completion of the last asynchronous read-back of THIS image */
+	float4* mirror = nullptr;    /* second destination of every pixel drawn (peer memory of the root replica), or NULL */
 };
 
 struct Context
@@ -96,6 +98,17 @@ struct VolumeImpl
 	size_t requestsValid = 0;                  /* requests on the device from the last reading sync */
 	size_t stagedRequests = 0;                 /* requests covered by the staging array (last compute phase) */
 	int    shardRank = 0, shardWorld = 1;
+
+	/* ---- multi-GPU over peer memory (DoonEngine/b200.h) ---- */
+	bool         peerAttached = false;
+	int          peerMode = 0;              /* DNb200peerMode */
+	DnbPeerTable peers;
+	size_t       peerRequestCap = 0;        /* requests every replica's staging array can hold */
+	uint32_t     peerEpoch = 0;             /* barriers issued so far; identical on every replica (SPMD) */
+	bool         peerFenceSinceCommit = false; /* a barrier has been passed since this replica's last commit */
+	bool         peerMergeUnfenced = false; /* peers may still be reading this replica's visible bitmap (merge not yet fenced) */
+	uint32_t     peerTimeoutsReported = 0;
+	DeviceArray<uint32_t> mailbox, barrierStatus;
 
 	DNb200stats stats;
 };

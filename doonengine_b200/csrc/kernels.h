@@ -18,12 +18,21 @@ typedef struct DnbUploadItem
 extern "C" {
 #endif
 
-cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, DnbHit* hits, cudaStream_t stream);
+/* mirror: second destination of every pixel (peer memory of the root replica), or NULL */
+cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, float4* mirror, DnbHit* hits, cudaStream_t stream);
 
 cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream);
-cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* staging, cudaStream_t stream);
+/* lights the 4-request CTAs  firstCta, firstCta + ctaStride, ...  of requests[0, numRequests) and stores the staged words of
+ * request r at word 96 r of every array in `targets` */
+cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+                             const DnbStagingTargets* targets, cudaStream_t stream);
+/* peers: NULL, or the table whose propagate bitmaps (all replicas') are ORed into visible instead of only the local one */
 cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
-                              unsigned long long* litCounter, cudaStream_t stream);
+                              unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream);
+
+/* peer.cu: device-side barrier over the replicas' mailboxes, and visible |= every peer's visible */
+cudaError_t dnb_launch_peer_barrier(const DnbPeerTable* peers, uint32_t epoch, uint32_t* status, cudaStream_t stream);
+cudaError_t dnb_launch_peer_or_visible(const DnbPeerTable* peers, uint32_t* visible, uint32_t words, cudaStream_t stream);
 
 uint32_t    dnb_compact_num_blocks(uint32_t numTiles);
 cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets, uint32_t* grandTotal,

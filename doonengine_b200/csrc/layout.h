@@ -103,8 +103,27 @@ typedef struct DnbDrawParams
 	float    invProjection[16];
 	uint32_t viewMode;
 	int32_t  width, height;      /* image size; (width/16)x(height/16) 16x16 groups are drawn (voxel.c:879) */
-	int32_t  rowBegin, rowEnd;   /* 16-pixel group rows [rowBegin, rowEnd) drawn by this launch (screen-tile split) */
+	int32_t  rowBegin, rowEnd;   /* 16-pixel group rows rowBegin, rowBegin+rowStride, ... < rowEnd are drawn by this launch */
+	int32_t  rowStride;          /* 1 = a contiguous band; world size = rows interleaved over the replicas (screen-tile split) */
 } DnbDrawParams;
+
+/* multi-GPU over peer memory (DoonEngine/b200.h): where replica r's exchange buffers are mapped in THIS process */
+#define DNB_MAX_PEERS 8
+typedef struct DnbPeerTable
+{
+	uint32_t        world, rank;
+	uint32_t*       staging[DNB_MAX_PEERS];
+	uint32_t*       mailbox[DNB_MAX_PEERS];
+	const uint32_t* visible[DNB_MAX_PEERS];
+	const uint32_t* propagate[DNB_MAX_PEERS];
+} DnbPeerTable;
+
+/* the staging arrays one lighting launch stores into: its own, or every replica's */
+typedef struct DnbStagingTargets
+{
+	uint32_t  count;
+	uint32_t* dst[DNB_MAX_PEERS];
+} DnbStagingTargets;
 
 /* random numbers of one lighting dispatch.  Every seed in voxelLighting.comp is a function of
  * (time, sample, bounce) only, never of the voxel (LI:75,162-168,259-260), so the host evaluates

@@ -15,6 +15,12 @@
  *
  * Staging layout: request r owns 96 words: [32 x w1][32 x w2][32 x w3] -> three fully coalesced 128-byte
  * stores per warp, and a contiguous byte range per rank for the multi-GPU all-gather.
+ *
+ * Multi-GPU over peer memory (DoonEngine/b200.h): the lighting kernel is given the staging array of EVERY replica
+ * (peer pointers mapped over NVLink) and stores each warp's three 128-byte rows into all of them as soon as the
+ * warp has finished tracing -- the exchange is fused into the kernel and overlaps the ray tracing of the other
+ * warps; no all-gather follows.  Replica `rank` of `world` runs the CTAs rank, rank + world, ... (interleaved, so
+ * expensive and cheap regions of the map spread evenly).
  */
 #include "kernels.h"
 #include "trace.cuh"
@@ -200,25 +206,37 @@ DNB_FN int nth_voxel(const uint32_t* mask, const uint16_t* prefix, uint32_t numV
 	return w * 32 + (int)__fns(mask[w], 0, (int)inWord + 1);
 }
 
+/* the three staged words of one voxel -> row `at` of every target array (1 target, or every replica's over NVLink) */
+DNB_FN void stage_words(const DnbStagingTargets& T, size_t at, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+	for(uint32_t p = 0; p < T.count; p++)
+	{
+		uint32_t* out = T.dst[p] + at;
+		out[0] = w1;
+		out[32] = w2;
+		out[64] = w3;
+	}
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* __restrict__ staging)
+__global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, DnbStagingTargets T)
 {
 	__shared__ DnbSlot s_slot[4];
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t r = firstRequest + blockIdx.x * 4 + warp;
-	if(r >= firstRequest + numRequests)
+	const uint32_t r = (firstCta + blockIdx.x * ctaStride) * 4 + warp;
+	if(r >= numRequests)
 		return;
 
 	const uint32_t request = __ldg(requests + r);
 	const uint32_t mapIndex = request >> 4;
-	uint32_t* out = staging + (size_t)r * 96u;
+	const size_t at = (size_t)r * 96u + lane;
 
 	const uint32_t slotId = __ldg(S.tileSlot + mapIndex) - 1u;
 	if(slotId == 0xFFFFFFFFu)
 	{
 		/* the chunk was removed between the request and the dispatch: nothing to light */
-		out[lane] = 0; out[32 + lane] = 0; out[64 + lane] = 0;
+		stage_words(T, at, 0, 0, 0);
 		return;
 	}
 
@@ -231,7 +249,7 @@ __global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_
 	const int local = nth_voxel(slot.mask, slot.prefix, slot.numVoxels, voxNum);
 	if(local < 0)
 	{
-		out[lane] = 0; out[32 + lane] = 0; out[64 + lane] = 0;
+		stage_words(T, at, 0, 0, 0);
 		return;
 	}
 
@@ -296,9 +314,10 @@ __global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_
 	const uint32_t wy = (uint32_t)rintf(diffuseLight.y * 65535.0f);
 	const uint32_t wz = (uint32_t)rintf(diffuseLight.z * 65535.0f);
 
-	out[lane]      = encode_rgba((uint32_t)rintf(albedo.x * 255.0f), (uint32_t)rintf(albedo.y * 255.0f), (uint32_t)rintf(albedo.z * 255.0f), (uint32_t)rintf(specLight.x * 255.0f));
-	out[32 + lane] = encode_rgba((uint32_t)rintf(specLight.y * 255.0f), (uint32_t)rintf(specLight.z * 255.0f), (wx >> 8) & 0xFFu, wx & 0xFFu);
-	out[64 + lane] = encode_rgba((wy >> 8) & 0xFFu, wy & 0xFFu, (wz >> 8) & 0xFFu, wz & 0xFFu);
+	stage_words(T, at,
+	            encode_rgba((uint32_t)rintf(albedo.x * 255.0f), (uint32_t)rintf(albedo.y * 255.0f), (uint32_t)rintf(albedo.z * 255.0f), (uint32_t)rintf(specLight.x * 255.0f)),
+	            encode_rgba((uint32_t)rintf(specLight.y * 255.0f), (uint32_t)rintf(specLight.z * 255.0f), (wx >> 8) & 0xFFu, wx & 0xFFu),
+	            encode_rgba((wy >> 8) & 0xFFu, wy & 0xFFu, (wz >> 8) & 0xFFu, wz & 0xFFu));
 
 	if(COUNT)
 	{
@@ -361,25 +380,39 @@ __global__ void dn_merge_visible_kernel(uint32_t* __restrict__ visible, uint32_t
 	}
 }
 
+/* the same over peer memory: visible |= every replica's propagate bitmap.  Nothing is cleared here -- the peers may still be
+ * reading this replica's bitmap; the host clears it at the start of the next lighting pass, behind a barrier (engine.cpp). */
+__global__ void dn_merge_visible_peers_kernel(DnbPeerTable T, uint32_t* __restrict__ visible, uint32_t numWords)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= numWords)
+		return;
+	uint32_t add = 0;
+	for(uint32_t p = 0; p < T.world; p++)
+		add |= *reinterpret_cast<const volatile uint32_t*>(T.propagate[p] + i);
+	if(add)
+		visible[i] |= add;
+}
+
 extern "C" cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream)
 {
 	return cudaMemcpyToSymbolAsync(c_light, params, sizeof(DnbLightParams), 0, cudaMemcpyHostToDevice, stream);
 }
 
-extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t firstRequest, uint32_t numRequests, uint32_t* staging, cudaStream_t stream)
+extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+                                        const DnbStagingTargets* targets, cudaStream_t stream)
 {
-	if(numRequests == 0)
+	if(numRequests == 0 || numCtas == 0)
 		return cudaSuccess;
-	const unsigned grid = (numRequests + 3) / 4;
 	if(scene->counters)
-		dn_light_kernel<true><<<grid, 128, 0, stream>>>(*scene, requests, firstRequest, numRequests, staging);
+		dn_light_kernel<true><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets);
 	else
-		dn_light_kernel<false><<<grid, 128, 0, stream>>>(*scene, requests, firstRequest, numRequests, staging);
+		dn_light_kernel<false><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets);
 	return cudaGetLastError();
 }
 
 extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
-                                         unsigned long long* litCounter, cudaStream_t stream)
+                                         unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream)
 {
 	if(numRequests > 0)
 	{
@@ -389,6 +422,9 @@ extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, 
 			return e;
 	}
 	const uint32_t words = (scene->numTiles + 31) / 32;
-	dn_merge_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(scene->visible, scene->propagate, words);
+	if(peers)
+		dn_merge_visible_peers_kernel<<<(words + 255) / 256, 256, 0, stream>>>(*peers, scene->visible, words);
+	else
+		dn_merge_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(scene->visible, scene->propagate, words);
 	return cudaGetLastError();
 }

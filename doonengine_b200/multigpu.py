@@ -1,6 +1,17 @@
 """One process per GPU: the map is replicated, the lighting-request list and the screen rows are sharded.
 
-Per frame, on every rank:
+Two exchange mechanisms:
+
+  exchange="peer" (default on GPUs)   the replicas map each other's exchange buffers (cudaIpc handles, swapped once through
+      torch.distributed) and from then on the plain frame calls run SPMD with NO collective on the frame path: the
+      lighting kernel stores its staged words into every replica's staging array over NVLink, the draw kernel mirrors
+      its pixels into the root's framebuffer, a device-side barrier kernel separates the phases and a merge kernel ORs
+      the peers' visible / propagate bitmaps (csrc/peer.cu, csrc/light.cu, csrc/draw.cu).  Rows and request CTAs are
+      interleaved over the ranks (rank, rank + world, ...).
+  exchange="collective"               host-driven all-gathers of contiguous slices through torch.distributed (NCCL on GPUs, gloo
+      in the CPU tests, where the oracle stands in for the device):
+
+Per frame, on every rank (collective mode):
 
     draw            each rank ray-casts its band of 16-pixel rows          (DN_draw with DN_b200_set_shard)
       exchange      all-gather the framebuffer bands; OR the ranks' visible bitmaps together
@@ -22,11 +33,22 @@ import numpy as np
 
 
 def request_slice(total, rank, world):
-    """(first, count, per_rank) of the contiguous request slice a rank lights; mirrors csrc/engine.cpp light_compute."""
-    per = (total + world - 1) // world
+    """(first, count, per_rank) of the contiguous request slice a rank lights in collective mode; mirrors csrc/engine.cpp
+    slice_len(): ceil(total / world) rounded up to whole 4-request CTAs."""
+    per = ((total + world - 1) // world + 3) & ~3
     first = min(total, per * rank)
     last = min(total, per * (rank + 1))
     return first, last - first, per
+
+
+def peer_ctas(total, rank, world):
+    """the 4-request CTAs replica `rank` lights in peer mode: rank, rank + world, ... (csrc/engine.cpp light_compute)."""
+    return range(rank, (total + 3) // 4, world)
+
+
+def peer_rows(group_rows, rank, world):
+    """the 16-pixel group rows replica `rank` draws in peer mode: rank, rank + world, ... (csrc/engine.cpp DN_draw)."""
+    return range(rank, group_rows, world)
 
 
 def row_band(group_rows, rank, world):
@@ -83,14 +105,95 @@ class _DevicePtr:
 class ShardedEngine:
     """drives one replica (a doonengine_b200.Engine) as rank `rank` of `world`."""
 
-    def __init__(self, engine, rank, world, torch, dist, device):
+    def __init__(self, engine, rank, world, torch, dist, device, exchange="peer"):
         from . import ARRAY_PROPAGATE, ARRAY_STAGING, ARRAY_VISIBLE
         self.e, self.rank, self.world, self.torch, self.dist, self.device = engine, rank, world, torch, dist, device
         self.L = engine.L
         self.A_VISIBLE, self.A_STAGING, self.A_PROPAGATE = ARRAY_VISIBLE, ARRAY_STAGING, ARRAY_PROPAGATE
-        if not self.L.DN_b200_set_shard(engine.vol, rank, world):
+        self.exchange = exchange if world > 1 else "none"
+        self._opened = []     # peer mappings to close
+        self._mirrors = {}    # fb -> opened root image
+        if self.exchange == "peer":
+            self._attach()
+        elif not self.L.DN_b200_set_shard(engine.vol, rank, world):
             raise ValueError("bad shard %d/%d" % (rank, world))
 
+    # ---- peer memory plumbing: done once (and again only if the staging arrays must grow) ----
+    def _all_gather_bytes(self, payload):
+        """every rank's `payload` (bytes, same length everywhere), as a list indexed by rank."""
+        t = self.torch.tensor(list(payload), dtype=self.torch.uint8, device=self.device)
+        out = self.torch.empty(len(payload) * self.world, dtype=self.torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
+        raw = bytes(out.cpu().numpy().tobytes())
+        return [raw[r * len(payload):(r + 1) * len(payload)] for r in range(self.world)]
+
+    def _attach(self, request_cap=0):
+        from . import PEER_AUTO, DNb200peerBuffers
+        L, e = self.L, self.e
+        mine = DNb200peerBuffers()
+        if not L.DN_b200_peer_prepare(e.vol, request_cap, C.byref(mine)):
+            raise RuntimeError("DN_b200_peer_prepare failed")
+        fields = ("staging", "mailbox", "visible", "propagate")
+        payload = b""
+        for f in fields:
+            h = C.create_string_buffer(64)
+            if not L.DN_b200_ipc_export(getattr(mine, f), h):
+                raise RuntimeError("DN_b200_ipc_export(%s) failed" % f)
+            payload += h.raw
+        payload += int(mine.stagingRequestCap).to_bytes(8, "little")
+        table = (DNb200peerBuffers * self.world)()
+        for r, raw in enumerate(self._all_gather_bytes(payload)):
+            if r == self.rank:
+                table[r] = mine
+                continue
+            for i, f in enumerate(fields):
+                ptr = L.DN_b200_ipc_open(raw[64 * i:64 * (i + 1)])
+                if not ptr:
+                    raise RuntimeError("DN_b200_ipc_open(%s of rank %d) failed: %s" % (f, r, _last_message()))
+                self._opened.append(ptr)
+                setattr(table[r], f, ptr)
+            table[r].stagingRequestCap = int.from_bytes(raw[256:264], "little")
+        if not L.DN_b200_peer_attach(e.vol, self.rank, self.world, table, PEER_AUTO):
+            raise RuntimeError("DN_b200_peer_attach failed: %s" % _last_message())
+        self.dist.barrier()  # nobody posts into a mailbox that is not attached yet
+
+    def _detach(self):
+        self.L.DN_b200_peer_detach(self.e.vol)
+        self.dist.barrier()  # every replica has stopped using the mappings
+        for fb in list(self._mirrors):
+            self.L.DN_b200_framebuffer_set_mirror(fb, None)
+        for ptr in self._opened:
+            self.L.DN_b200_ipc_close(ptr)
+        self._opened, self._mirrors = [], {}
+
+    def mirror_framebuffer(self, fb, root=0):
+        """peer mode: every pixel this rank draws into `fb` is also stored into the root's framebuffer of the same size."""
+        if self.exchange != "peer":
+            return
+        L = self.L
+        h = C.create_string_buffer(64)
+        if self.rank == root and not L.DN_b200_ipc_export(L.DN_b200_framebuffer_device_ptr(fb), h):
+            raise RuntimeError("DN_b200_ipc_export(framebuffer) failed")
+        raw = self._all_gather_bytes(h.raw)[root]
+        if self.rank != root:
+            ptr = L.DN_b200_ipc_open(raw)
+            if not ptr:
+                raise RuntimeError("DN_b200_ipc_open(framebuffer) failed: %s" % _last_message())
+            self._opened.append(ptr)
+            self._mirrors[fb] = ptr
+            L.DN_b200_framebuffer_set_mirror(fb, ptr)
+        self.dist.barrier()
+
+    def close(self):
+        if self.exchange == "peer" and self.e.vol:
+            self._detach()
+
+    def barrier_status(self):
+        ep, to = C.c_uint64(), C.c_uint32()
+        self.L.DN_b200_peer_barrier_status(self.e.vol, C.byref(ep), C.byref(to))
+        return int(ep.value), int(to.value)
+
+    # ---- helpers of the collective mode ----
     def _tensor(self, ptr, nbytes):
         return self.torch.as_tensor(_DevicePtr(ptr, nbytes), device=self.device)
 
@@ -98,11 +201,13 @@ class ShardedEngine:
         nbytes = self.L.DN_b200_array_bytes(self.e.vol, which)
         return self._tensor(self.L.DN_b200_array_device_ptr(self.e.vol, which), nbytes)
 
+    # ---- frame ----
     def draw(self, fb, view, proj):
-        """DN_draw of this rank's band + exchange; afterwards every rank holds the whole image and all visible bits."""
+        """DN_draw of this rank's rows + exchange.  Afterwards every rank holds all visible bits; the whole image is on every
+        rank (collective mode) or on the root of a mirrored framebuffer (peer mode)."""
         L, e = self.L, self.e
         L.DN_draw(e.vol, fb, view, proj, -1, -1)
-        if self.world == 1:
+        if self.exchange != "collective":
             return
         w, h = C.c_int(), C.c_int()
         L.DN_b200_framebuffer_size(fb, C.byref(w), C.byref(h))
@@ -116,12 +221,17 @@ class ShardedEngine:
         self.L.DN_sync_gpu(self.e.vol, op, split)
 
     def light_compute(self, num_diffuse, max_diffuse, time):
+        if self.exchange == "peer" and not self.L.DN_b200_peer_capacity_ok(self.e.vol):
+            # the request list outgrew the staging arrays (identically on every rank): remap with room to spare
+            need = int(self.e.vol.contents.numLightingRequests)
+            self._detach()
+            self._attach(request_cap=2 * need + 4096)
         if not self.L.DN_b200_light_compute(self.e.vol, num_diffuse, max_diffuse, C.c_float(time)):
-            raise RuntimeError("DN_b200_light_compute failed")
+            raise RuntimeError("DN_b200_light_compute failed: %s" % _last_message())
 
     def light_exchange(self):
-        if self.world == 1:
-            return
+        if self.exchange != "collective":
+            return  # peer mode: the lighting kernel has already stored into every replica
         L, e = self.L, self.e
         slice_bytes = L.DN_b200_staging_slice_bytes(e.vol)
         if slice_bytes:
@@ -138,3 +248,9 @@ class ShardedEngine:
         self.light_compute(num_diffuse, max_diffuse, time)
         self.light_exchange()
         self.light_commit()
+
+
+def _last_message():
+    from . import messages
+    m = messages()
+    return m[-1][2] if m else "?"

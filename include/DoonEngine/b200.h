@@ -35,7 +35,8 @@ bool   DN_b200_read_framebuffer(GLuint fb, float* dst, size_t bytes); /* synchro
 bool   DN_b200_clear_framebuffer(GLuint fb, float value);
 /* asynchronous read-back on a side stream: ordered after the work queued so far, overlaps with what is queued next */
 bool   DN_b200_read_framebuffer_async(GLuint fb, float* dst, size_t bytes);
-bool   DN_b200_wait_framebuffer(void);
+bool   DN_b200_wait_framebuffer(void);            /* every read-back queued so far */
+bool   DN_b200_wait_framebuffer_read(GLuint fb);  /* the last read-back of this framebuffer only */
 
 /* per-pixel first-hit capture for parity tests: status 0 box miss / 1 no hit / 2 hit, tile, voxel, record-in-chunk */
 typedef struct DNb200hit { int32_t status; uint32_t mapIndex, localIndex, recordIndex; } DNb200hit;
@@ -95,6 +96,56 @@ size_t DN_b200_staging_slice_bytes(DNvolume* vol);
 /* bitmap[] |= other[] for a bitmap gathered from another rank (device pointer, same length); `which` is
  * DN_B200_VISIBLE (after a sharded draw) or DN_B200_PROPAGATE (after a sharded lighting compute phase) */
 bool   DN_b200_or_bitmap(DNvolume* vol, DNb200array which, const void* deviceBitmap);
+
+/* ---- multi-GPU over peer memory (NVLink / NVSwitch): the kernels exchange their results themselves ----
+ * Replaces the host-driven all-gathers above.  Every replica maps the others' exchange buffers (cudaIpc handles
+ * between processes, plain device pointers inside one process) and then the ordinary frame calls run SPMD:
+ *   DN_draw            draws the 16-pixel rows  rank, rank+world, ...  (interleaved: balances sky against terrain),
+ *                      stores each pixel into its own framebuffer AND the framebuffer's mirror (peer memory of the
+ *                      root replica) from inside the kernel; then a device-side barrier over NVLink and a merge
+ *                      kernel that ORs the peers' visible bitmaps into this replica's
+ *   DN_sync_gpu        unchanged: every replica compacts the identical bitmap into the identical request list
+ *   DN_update_lighting lights request CTAs  rank, rank+world, ...  and stores the three staged words of every voxel
+ *                      straight into EVERY replica's staging array (peer stores from the lighting kernel, so the
+ *                      exchange overlaps the ray tracing); device-side barrier; every replica commits everything
+ * Results are bit-identical to the unsharded run for any number of replicas (snapshot semantics, oracle.h N1-N3).
+ * No host synchronisation and no NCCL call is on the frame path; the barrier is a one-CTA kernel that posts an epoch
+ * word into every peer's mailbox (st.release.sys) and spins on its own (ld.acquire.sys), bounded by a time-out. */
+#define DN_B200_MAX_PEERS 8
+typedef struct DNb200peerBuffers
+{
+	void* staging;   /* uint32[96 * stagingRequestCap]: lit words, written by every replica */
+	void* mailbox;   /* uint32[DN_B200_MAX_PEERS]: barrier epochs, slot r written by replica r */
+	void* visible;   /* this replica's visible bitmap (read by the peers' merge kernel) */
+	void* propagate; /* this replica's propagate bitmap (read by the peers' commit) */
+	uint64_t stagingRequestCap;
+} DNb200peerBuffers;
+typedef enum DNb200peerMode
+{
+	DN_B200_PEER_AUTO   = 0, /* one process per GPU: DN_draw / DN_update_lighting run the barriers and merges themselves */
+	DN_B200_PEER_MANUAL = 1  /* several replicas driven by ONE host thread on one stream (tests): no device barriers; the host
+	                            sequences the phases with DN_b200_peer_exchange_visible / DN_b200_light_compute / DN_b200_light_commit */
+} DNb200peerMode;
+/* sizes this replica's exchange buffers for `requestCap` lighting requests (0 = every resident chunk fully lit, plus slack) and
+ * returns their device pointers; call after the map is resident and before exporting handles */
+bool  DN_b200_peer_prepare(DNvolume* vol, size_t requestCap, DNb200peerBuffers* mine);
+/* cudaIpcGetMemHandle / cudaIpcOpenMemHandle(lazy peer access) / cudaIpcCloseMemHandle on 64-byte opaque handles */
+bool  DN_b200_ipc_export(const void* devicePtr, void* handle64);
+void* DN_b200_ipc_open(const void* handle64);
+bool  DN_b200_ipc_close(void* devicePtr);
+/* peers[world]: entry r = replica r's buffers as seen from THIS process (entry `rank` = the result of peer_prepare) */
+bool  DN_b200_peer_attach(DNvolume* vol, int rank, int worldSize, const DNb200peerBuffers* peers, DNb200peerMode mode);
+void  DN_b200_peer_detach(DNvolume* vol);
+/* false when the request list of the last reading sync no longer fits the attached staging arrays (all replicas see the
+ * same answer): detach, prepare with a larger capacity, exchange handles and attach again */
+bool  DN_b200_peer_capacity_ok(DNvolume* vol);
+/* every pixel DN_draw writes into `fb` is also stored to `mirrorImage` (same size, usually the root replica's framebuffer
+ * in peer memory); NULL = off.  The root must not read a mirrored framebuffer before the post-draw barrier. */
+bool  DN_b200_framebuffer_set_mirror(GLuint fb, void* mirrorImage);
+/* DN_B200_PEER_MANUAL only: visible |= every peer's visible (call once every replica has drawn) */
+bool  DN_b200_peer_exchange_visible(DNvolume* vol);
+/* epochs completed and time-outs seen by this replica's device barrier (a time-out is also reported through the callback) */
+bool  DN_b200_peer_barrier_status(DNvolume* vol, uint64_t* epochs, uint32_t* timeouts);
 
 #ifdef __cplusplus
 }

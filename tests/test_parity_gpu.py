@@ -336,3 +336,97 @@ def test_staging_words_match_oracle(dn, oracle_mod):
     assert got.shape == want.shape and np.array_equal(got, want)
     e.close()
     o.close()
+
+
+def test_peer_sharded_equals_unsharded(dn, oracle_mod):
+    """multi-GPU over peer memory (b200.h), single-process form: three replicas on one GPU are attached to each other with
+    plain device pointers (DN_B200_PEER_MANUAL: no device barrier, this thread sequences the phases).  Each replica draws its
+    interleaved rows and mirrors them into replica 0's framebuffer from inside the draw kernel, lights its interleaved
+    request CTAs and stores the staged words into EVERY replica's staging array from inside the lighting kernel.  After
+    every frame all replicas must be bit-identical to an unsharded engine, which must match the oracle."""
+    import ctypes as C
+    from doonengine_b200 import scenes
+    tiles = (6, 4, 6)
+    world = 3
+    reps = [dn.Engine(map_size=tiles, min_chunks=64) for _ in range(world)]
+    whole = dn.Engine(map_size=tiles, min_chunks=64)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    for eng in reps + [whole, o]:
+        scenes.build(eng, scenes.mixed_materials(tiles), **scenes.mixed_camera(tiles))
+        eng.sync(1, 1)
+    L = whole.L
+    table = (dn.DNb200peerBuffers * world)()
+    for r, e in enumerate(reps):
+        assert L.DN_b200_peer_prepare(e.vol, 0, C.byref(table[r]))
+    for r, e in enumerate(reps):
+        assert L.DN_b200_peer_attach(e.vol, r, world, table, dn.PEER_MANUAL)
+
+    w, h = W, H
+    fbs = [e.framebuffer(w, h) for e in reps]
+    root_image = L.DN_b200_framebuffer_device_ptr(fbs[0])
+    for r in range(1, world):
+        assert L.DN_b200_framebuffer_set_mirror(fbs[r], root_image)
+
+    for k in range(4):
+        for e, fb in zip(reps, fbs):
+            L.DN_b200_clear_framebuffer(fb, 0.0)
+        for e in reps:
+            e.draw_async(w, h)
+        for e in reps:
+            assert L.DN_b200_peer_exchange_visible(e.vol)
+        ref_img = whole.draw(w, h)
+        got = reps[0].read_framebuffer(fbs[0])
+        assert np.array_equal(got.view(np.uint32), ref_img.view(np.uint32)), "frame %d: the root's mirrored image differs from the unsharded draw" % k
+        # a non-root replica holds exactly its own rows
+        mine = reps[1].read_framebuffer(fbs[1])
+        for g in range(h // 16):
+            rows = slice(16 * g, 16 * g + 16)
+            if g % world == 1:
+                assert np.array_equal(mine[rows].view(np.uint32), ref_img[rows].view(np.uint32))
+            else:
+                assert not mine[rows].any()
+        assert_images_close(ref_img, o.draw(w, h), "frame %d" % k)
+
+        for eng in reps + [whole, o]:
+            eng.sync(2, 1)
+        want = o.requests()
+        for eng in reps + [whole]:
+            assert np.array_equal(eng.requests(), want)
+
+        for e in reps:
+            assert L.DN_b200_light_compute(e.vol, 1, 1000, frame_time(k))
+        for e in reps:
+            assert L.DN_b200_light_commit(e.vol)
+        whole.update_lighting(1, 1000, frame_time(k))
+        o.update_lighting(1, 1000, frame_time(k))
+
+        ref_state = records_by_tile(whole)
+        _compare_state(whole, records_by_tile(o), "frame %d (unsharded vs oracle)" % k)
+        for r, e in enumerate(reps):
+            st_r = records_by_tile(e)
+            for key in ref_state:
+                assert np.array_equal(st_r[key], ref_state[key]), "frame %d: %s of replica %d differs from the unsharded engine" % (k, key, r)
+    for e in reps:
+        L.DN_b200_peer_detach(e.vol)
+    for eng in reps + [whole, o]:
+        eng.close()
+
+
+def test_peer_processes_device_barrier(dn, oracle_mod):
+    """the real thing: one PROCESS per replica (torch.distributed only swaps the cudaIpc handles), DN_B200_PEER_AUTO, the
+    device-side barrier kernel between the phases.  Uses as many GPUs as the box has (2 replicas share one GPU on a 1-GPU
+    box: IPC mappings and the barrier still work, the kernels of the two processes are time-sliced)."""
+    import socket
+    import subprocess
+    import sys
+    from conftest import ROOT
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "peer_worker.py")]
+    p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:]
+    assert "peer-sharded == unsharded" in p.stdout
