@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     # name: (scene, tiles, (w, h), description)
     "c2": ("terrain", (64, 64, 64), (1920, 1080), "synthetic procedural terrain 512^3 voxels (64^3 chunks), 1920x1080"),
+    "c4": ("terrain", (64, 64, 64), (1920, 1080), "edit-heavy streaming: 10k random voxel edits/frame with partial chunk re-upload on the 512^3 terrain map, 1920x1080"),
     "c1": ("demo", (10, 3, 10), (1280, 720), "bundled demo map (tests/golden/demo.voxvol), 1280x720"),
     "c3s": ("sparse", (128, 128, 128), (3840, 2160), "synthetic sparse 1024^3 map (~20% chunks occupied), 3840x2160 (config 3 at 1/8 volume)"),
     "c5s": ("dense", (32, 32, 32), (3840, 2160), "dense 256^3 map, specular-heavy, corridors, 3840x2160 (config 5 at 1/64 volume)"),
@@ -47,6 +48,23 @@ UNIT = "voxel-updates/s"
 
 def frame_time(k):
     return float(np.float32(1.0) + np.float32(k) / np.float32(60.0))
+
+
+EDITS_PER_FRAME = 10000
+
+
+def frame_edits(k, tiles, n=EDITS_PER_FRAME):
+    """config 4's edit stream of frame k: n positions uniform in the voxel box; half remove (material 255),
+    half set {material 0, hashed albedo, normal (0,1,0)}.  Counter-based hash, so every rank builds the identical stream."""
+    from doonengine_b200 import scenes
+    i = np.arange(n, dtype=np.uint64) + np.uint64(k) * np.uint64(n)
+    pos = np.stack([scenes.pcg_hash((i * np.uint64(3) + np.uint64(a) + np.uint64(7 << 20)) & np.uint64(0xFFFFFFFF)).astype(np.int64) % (tiles[a] * 8) for a in range(3)], axis=1).astype(np.int32)
+    h = scenes.pcg_hash((i + np.uint64(0x5EED0000)) & np.uint64(0xFFFFFFFF))
+    remove = (h & np.uint32(1)) == 0
+    up = scenes.normal_word(np.zeros(n, np.uint32), np.tile(np.array([0.0, 1.0, 0.0], np.float32), (n, 1)))
+    normal = np.where(remove, np.uint32(0xFFFFFFFF), up).astype(np.uint32)
+    albedo = scenes.albedo_word(32 + (h >> np.uint32(8)) % np.uint32(209), 32 + (h >> np.uint32(16)) % np.uint32(209), 32 + (h >> np.uint32(24)) % np.uint32(209)).astype(np.uint32)
+    return pos, np.stack([normal, albedo], axis=1)
 
 
 def make_chunks(scene, tiles):
@@ -245,6 +263,7 @@ def run_ours(args, scene, tiles, res, desc):
     w, h = res
     L = dn.lib()
     dn.init(device=local)
+    L.DN_b200_set_light_kernel(1 if args.light_kernel == "flat" else 0)
     # a non-default stream shared by torch (events, collectives, copies) and the library's kernels
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
@@ -272,24 +291,55 @@ def run_ours(args, scene, tiles, res, desc):
     for f in fbs:
         sh.mirror_framebuffer(f, root=0)
     fb_bytes = w * h * 16
-    host_images = [torch.empty(fb_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(3)] if rank == 0 else None
+    # host side of the end-to-end path: three whole-frame buffers in pinned memory.  N > 1: ONE POSIX shared-memory mapping,
+    # page-locked in every replica's process -- each GPU copies the rows it drew over its own PCIe link and the frame is
+    # assembled in host memory (no NVLink hop, no root bottleneck)
+    shm_path, shm_map = None, None
+    if world == 1:
+        host_pinned = torch.empty(3 * fb_bytes, dtype=torch.uint8, pin_memory=True)
+        host_base = host_pinned.data_ptr()
+    else:
+        import mmap
+        name = ["/dev/shm/dnb200_frames_%d_%d" % (os.getpid(), int(time.time() * 1e6))] if rank == 0 else [None]
+        if rank == 0:
+            with open(name[0], "wb") as f:
+                f.truncate(3 * fb_bytes)
+        dist.broadcast_object_list(name, src=0)
+        shm_path = name[0]
+        fd = os.open(shm_path, os.O_RDWR)
+        shm_map = mmap.mmap(fd, 3 * fb_bytes)
+        os.close(fd)
+        host_base = C.addressof(C.c_char.from_buffer(shm_map))
+        if not L.DN_b200_host_register(host_base, 3 * fb_bytes):
+            raise SystemExit("DN_b200_host_register failed: %s" % (dn.messages()[-1][2] if dn.messages() else "?"))
+        dist.barrier()
+    host_ptrs = [host_base + i * fb_bytes for i in range(3)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
     view, proj = e.view_projection(h / w)
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
+    # config 4: the edits of every frame, generated before anything is timed
+    edit_stream, edit_host_s = None, [0.0]
+    if args.config == "c4":
+        edit_stream = [frame_edits(k, tiles) for k in range(args.warmup + 2 * args.steps + 1)]
+
     def step(k, timed, read_back):
         """one frame; returns the events bracketing its phases."""
         marks = [ev() for _ in range(6)] if timed else None
         fb = fbs[k % 3]
-        read_back = read_back and rank == 0  # the whole image is assembled on the root (mirrored pixel stores)
+        if edit_stream is not None:
+            t_e = time.perf_counter()
+            e.set_voxels(*edit_stream[k])
+            edit_host_s[0] += time.perf_counter() - t_e
         if timed:
             marks[0].record(stream)
         sh.draw(fb, view, proj)
         if read_back:
-            # the copy to pinned host memory runs on a side stream, overlapped with compaction, lighting and the next draw
-            L.DN_b200_read_framebuffer_async(fb, host_images[k % 3].data_ptr(), fb_bytes)
+            # the copy of this replica's rows to pinned host memory runs on a side stream, overlapped with compaction, lighting
+            # and the next draw
+            L.DN_b200_read_framebuffer_rows_async(fb, e.vol, host_ptrs[k % 3], fb_bytes)
         if timed:
             marks[1].record(stream)
         L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
@@ -322,6 +372,8 @@ def run_ours(args, scene, tiles, res, desc):
             sampler.start()
         all_marks, reqs = [], 0
         wall0 = time.perf_counter()
+        region0 = ev()
+        region0.record(stream)
         for i in range(steps):
             flush.fill_(i & 0xFF)
             m, r = step(k0 + i, True, read_back)
@@ -329,7 +381,7 @@ def run_ours(args, scene, tiles, res, desc):
             reqs += r
         drain0, drain1 = ev(), ev()
         drain0.record(stream)
-        if read_back and rank == 0:
+        if read_back:
             L.DN_b200_wait_framebuffer()  # the last frame's pixels
         drain1.record(stream)
         barrier()
@@ -341,8 +393,12 @@ def run_ours(args, scene, tiles, res, desc):
                 phases[j] += m[j].elapsed_time(m[j + 1])
         phases[4] += drain0.elapsed_time(drain1)
         lit = e.stats()["voxelsLit"] - lit0
+        # [5] whole step, [6] lighting phases: summed per rank BEFORE the max over ranks (a per-phase max would count a wait twice)
+        # [7] the whole region in one piece, L2 flushes and host gaps included: what the end-to-end number is quoted on
+        phases = np.concatenate([phases, [phases.sum(), phases[2] + phases[3], region0.elapsed_time(drain1)]])
         return phases, lit, reqs, clocks, wall
 
+    stats0 = e.stats()
     # ---- warm-up ----
     for k in range(args.warmup):
         step(k, False, False)
@@ -363,12 +419,11 @@ def run_ours(args, scene, tiles, res, desc):
     phases = reduce_max(phases)
     phases2 = reduce_max(phases2)
     K = max(args.steps, 1)
-    draw_ms, sync_ms, light_ms, commit_ms, rb_ms = (phases / K).tolist()
-    frame_ms = draw_ms + sync_ms + light_ms + commit_ms
-    frame2_ms = float(phases2.sum() / K)
-    light_total_s = (phases[2] + phases[3]) / 1000.0
+    draw_ms, sync_ms, light_ms, commit_ms, rb_ms, frame_ms, light_total_ms, _ = (phases / K).tolist()
+    frame2_ms = float(phases2[7] / K)
+    light_total_s = phases[6] / 1000.0
     value = lit / light_total_s if light_total_s > 0 else 0.0
-    e2e_value = lit2 / (phases2.sum() / 1000.0) if phases2.sum() > 0 else 0.0
+    e2e_value = lit2 / (phases2[7] / 1000.0) if phases2[7] > 0 else 0.0
 
     # ---- one instrumented frame (untimed) for the algorithmic byte count ----
     roofline = None
@@ -398,7 +453,7 @@ def run_ours(args, scene, tiles, res, desc):
         achieved = b_light / (light_ms / 1000.0) / 1e9 if light_ms > 0 else 0.0
         b_draw = algorithmic_bytes_draw(cd)
         traffic = traffic_from_profile()
-        roofline = {"kernel": "dn_light_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        roofline = {"kernel": "dn_light_flat_kernel" if args.light_kernel == "flat" else "dn_light_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                     "algorithmic_bytes_per_launch": b_light, "compulsory_bytes_per_launch": b_compulsory,
                     "compulsory_frac": (b_compulsory / (light_ms / 1000.0) / 1e9 / peak) if light_ms > 0 else 0.0,
@@ -416,6 +471,14 @@ def run_ours(args, scene, tiles, res, desc):
 
     if rank == 0:
         stats = e.stats()
+        edits = None
+        if edit_stream is not None:
+            frames_run = args.warmup + 2 * args.steps + 1
+            edits = {"edits_per_step": EDITS_PER_FRAME, "host_apply_ms_per_step": 1000.0 * edit_host_s[0] / frames_run,
+                     "chunks_uploaded_per_step": (stats["chunksUploaded"] - stats0["chunksUploaded"]) / frames_run,
+                     "bytes_uploaded_per_step": (stats["bytesUploaded"] - stats0["bytesUploaded"]) / frames_run,
+                     "edits_per_s_end_to_end": EDITS_PER_FRAME / (frame2_ms / 1000.0) if frame2_ms > 0 else 0.0,
+                     "note": "sync_compact includes the host-side packing of the dirty chunks and their upload on the side stream"}
         # draw, compaction count + scan + write, lighting, commit, visible merge; peer mode adds 2 barriers + the visible-bitmap merge,
         # collective mode one OR kernel per rank and bitmap
         launches_per_step = 7 if world == 1 else (10 if sh.exchange == "peer" else 7 + 2 * world)
@@ -423,21 +486,30 @@ def run_ours(args, scene, tiles, res, desc):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "parallelism": ("map replicated, request CTAs and 16-pixel rows interleaved x%d, exchange=%s" % (world, sh.exchange)) if world > 1 else "1 GPU",
-                       "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
+                       "light_kernel": "dn_light_flat_kernel" if args.light_kernel == "flat" else "dn_light_kernel", "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
                        "resident_records": int(stats["residentRecords"]), "requests_per_step": reqs / K, "voxels_lit_per_step": lit / K, "build_s": t_build},
             "frame_ms": {"draw": draw_ms, "sync_compact": sync_ms, "light_kernel": light_ms, "commit": commit_ms, "frame": frame_ms, "frame_with_readback": frame2_ms,
                          "wall_per_step_incl_flush": 1000.0 * wall / K},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8192 + 2416, "d2h_bytes_per_step": fb_bytes + 4, "ms_per_step": frame2_ms,
-                    "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps frame k+1; the last copy is drained inside the timed region)"},
+                    "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps frame k+1; N > 1: every replica copies the rows it drew into one shared pinned mapping); timed as ONE region from the first draw to the last copy landing, L2 flushes and host gaps between steps included"},
             "gpu_launches": launches_per_step * args.steps * 2,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if edits:
+            out["edits"] = edits
+            out["e2e"]["h2d_bytes_per_step"] += int(edits["bytes_uploaded_per_step"])
         print(json.dumps(out), flush=True)
     if world > 1:
         ep, to = sh.barrier_status() if sh.exchange == "peer" else (0, 0)
         if to:
             print("rank %d: %d device-barrier time-outs -- results invalid" % (rank, to), file=sys.stderr, flush=True)
     sh.close()
+    if shm_map is not None:
+        e.synchronize()
+        L.DN_b200_host_unregister(host_base)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(shm_path)
     for f in fbs:
         L.DN_b200_delete_framebuffer(f)
     e.close()
@@ -453,8 +525,9 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--light-kernel", default="flat", choices=["flat", "warp"], help="persistent state-machine lighting kernel (default) or one warp per request")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"], help="N > 1: kernels exchange over peer memory (default) or host-driven NCCL all-gathers")
-    ap.add_argument("--sampler-ms", type=float, default=20.0, help="NVML clock sampling period during the timed region (0 = off)")
+    ap.add_argument("--sampler-ms", type=float, default=10.0, help="NVML clock sampling period during the timed region (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -160,10 +160,16 @@ _PROTOTYPES = {
     "DN_b200_read_framebuffer": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
     "DN_b200_clear_framebuffer": (C.c_bool, [C.c_uint32, C.c_float]),
     "DN_b200_read_framebuffer_async": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
+    "DN_b200_read_framebuffer_rows_async": (C.c_bool, [C.c_uint32, C.POINTER(DNvolume), C.c_void_p, C.c_size_t]),
+    "DN_b200_host_register": (C.c_bool, [C.c_void_p, C.c_size_t]),
+    "DN_b200_host_unregister": (C.c_bool, [C.c_void_p]),
     "DN_b200_wait_framebuffer": (C.c_bool, []),
     "DN_b200_wait_framebuffer_read": (C.c_bool, [C.c_uint32]),
     "DN_b200_capture_hits": (C.c_bool, [C.c_uint32, C.c_bool]),
     "DN_b200_read_hits": (C.c_bool, [C.c_uint32, C.c_void_p, C.c_size_t]),
+    "DN_b200_set_light_kernel": (None, [C.c_int]),
+    "DN_b200_get_light_kernel": (C.c_int, []),
+    "DN_b200_set_flat_tuning": (None, [C.c_int, C.c_int, C.c_int]),
     "DN_b200_fetch_lighting_requests": (C.c_size_t, [C.POINTER(DNvolume)]),
     "DN_b200_array_bytes": (C.c_size_t, [C.POINTER(DNvolume), C.c_int]),
     "DN_b200_download": (C.c_size_t, [C.POINTER(DNvolume), C.c_int, C.c_void_p, C.c_size_t]),
@@ -174,6 +180,7 @@ _PROTOTYPES = {
     "DN_b200_enable_timing": (None, [C.c_bool]),
     "DN_b200_touch_tile": (None, [C.POINTER(DNvolume), DNivec3]),
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
+    "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
     "DN_b200_set_shard": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int]),
     "DN_b200_light_compute": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int, C.c_float]),
     "DN_b200_light_commit": (C.c_bool, [C.POINTER(DNvolume)]),
@@ -356,6 +363,13 @@ class Engine:
         ch["numVoxels"][ci] = n
         ch["updated"][ci] = 1
         self.L.DN_b200_touch_tile(self.vol, mp)
+
+    def set_voxels(self, positions, voxels):
+        """bulk edits: positions int32 [n,3] in voxel units, voxels uint32 [n,2] (normal word, albedo word); material 255 removes."""
+        p = np.ascontiguousarray(positions, dtype=np.int32)
+        v = np.ascontiguousarray(voxels, dtype=np.uint32)
+        assert p.ndim == 2 and p.shape[1] == 3 and v.shape == (p.shape[0], 2)
+        return int(self.L.DN_b200_set_voxels(self.vol, p.shape[0], p.ctypes.data, v.ctypes.data))
 
     def compress_voxel(self, material, normal, albedo):
         r = self.L.DN_compress_voxel(DNvoxel(material, DNvec3(*normal), DNcolor(*albedo)))

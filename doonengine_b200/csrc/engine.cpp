@@ -798,6 +798,60 @@ extern "C" bool DN_b200_read_framebuffer_async(GLuint id, float* dst, size_t byt
 	return ok;
 }
 
+/* The same for the rows THIS replica of a sharded volume drew (peer mode: 16-pixel group rows rank, rank + world, ...;
+ * host-driven mode: its band): `dst` is the whole-image buffer, preferably pinned memory shared by all the replicas' processes
+ * (DN_b200_host_register on a shared mapping) -- every GPU then sends its share over its own PCIe link and the frame is
+ * assembled in host memory without crossing NVLink. */
+extern "C" bool DN_b200_read_framebuffer_rows_async(GLuint id, DNvolume* vol, float* dst, size_t bytes)
+{
+	Framebuffer* fb = find_fb(id);
+	const size_t need = fb ? (size_t)fb->width * fb->height * sizeof(float4) : 0;
+	if(!fb || !vol || bytes < need)
+		return false;
+	VolumeImpl* v = impl_of(vol);
+	Context& c = ctx();
+	const size_t groupBytes = (size_t)16 * fb->width * sizeof(float4);
+	const int groupRows = fb->height / 16;
+	int begin = 0, end = groupRows, stride = 1;
+	if(v->peerAttached)
+	{
+		begin = v->shardRank;
+		stride = v->shardWorld;
+	}
+	else if(v->shardWorld > 1)
+	{
+		const int per = (groupRows + v->shardWorld - 1) / v->shardWorld;
+		begin = std::min(groupRows, per * v->shardRank);
+		end = std::min(groupRows, per * (v->shardRank + 1));
+	}
+	bool ok = cuda_ok(cudaEventRecord(c.evDrawDone, c.stream()), "event record");
+	ok = ok && cuda_ok(cudaStreamWaitEvent(c.readStream, c.evDrawDone, 0), "stream wait");
+	const int count = end > begin ? (end - begin + stride - 1) / stride : 0;
+	if(ok && count > 0)
+	{
+		const size_t at = (size_t)begin * groupBytes;
+		ok = cuda_ok(cudaMemcpy2DAsync((char*)dst + at, groupBytes * stride, (const char*)fb->image + at, groupBytes * stride, groupBytes, (size_t)count, cudaMemcpyDeviceToHost, c.readStream),
+		             "framebuffer rows read");
+	}
+	ok = ok && cuda_ok(cudaEventRecord(c.evReadDone, c.readStream), "event record");
+	if(ok && !fb->evRead)
+		ok = cuda_ok(cudaEventCreateWithFlags(&fb->evRead, cudaEventDisableTiming), "event create");
+	ok = ok && cuda_ok(cudaEventRecord(fb->evRead, c.readStream), "event record");
+	fb->readPending = true;
+	return ok;
+}
+
+/* pins (page-locks) caller-owned host memory, e.g. a POSIX shared-memory mapping several replica processes write one frame into */
+extern "C" bool DN_b200_host_register(void* ptr, size_t bytes)
+{
+	return ctx().ready && cuda_ok(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable), "cudaHostRegister");
+}
+
+extern "C" bool DN_b200_host_unregister(void* ptr)
+{
+	return ctx().ready && cuda_ok(cudaHostUnregister(ptr), "cudaHostUnregister");
+}
+
 extern "C" bool DN_b200_wait_framebuffer(void)
 {
 	return cuda_ok(cudaStreamSynchronize(ctx().readStream), "framebuffer read");
@@ -967,6 +1021,22 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 	}
 }
 
+/* which lighting kernel runs: 0 = one warp per request (light.cu), 1 = persistent state machine (light_flat.cuh).
+ * Default from $DN_B200_LIGHT_KERNEL ("warp" / "flat"), overridden by DN_b200_set_light_kernel. */
+static int g_lightKernel = -1;
+static int light_kernel_choice()
+{
+	if(g_lightKernel < 0)
+	{
+		const char* env = getenv("DN_B200_LIGHT_KERNEL");
+		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : 1;
+	}
+	return g_lightKernel;
+}
+
+extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = which ? 1 : 0; }
+extern "C" int DN_b200_get_light_kernel(void) { return light_kernel_choice(); }
+
 static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSamples, float time)
 {
 	DNvolume* vol = &v->pub;
@@ -1071,7 +1141,7 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
 	/* a slice that is not the last one ends on a CTA boundary (slice_len is a multiple of 4); the last CTA of the list is cut by numRequests */
 	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
-	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, s), "lighting kernel");
+	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, light_kernel_choice() == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
 	return ok;
 }
 

@@ -23,9 +23,11 @@ cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, 
 
 cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream);
 /* lights the 4-request CTAs  firstCta, firstCta + ctaStride, ...  of requests[0, numRequests) and stores the staged words of
- * request r at word 96 r of every array in `targets` */
+ * request r at word 96 r of every array in `targets`.
+ * flatCounter: NULL = dn_light_kernel (one warp per request); else a device word used as the work counter of the persistent
+ * state-machine kernel dn_light_flat_kernel (light_flat.cuh).  Both give identical results. */
 cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
-                             const DnbStagingTargets* targets, cudaStream_t stream);
+                             const DnbStagingTargets* targets, uint32_t* flatCounter, cudaStream_t stream);
 /* peers: NULL, or the table whose propagate bitmaps (all replicas') are ORed into visible instead of only the local one */
 cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
                               unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream);

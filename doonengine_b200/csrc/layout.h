@@ -118,6 +118,12 @@ typedef struct DnbPeerTable
 	const uint32_t* propagate[DNB_MAX_PEERS];
 } DnbPeerTable;
 
+/* scheduling knobs of the persistent lighting kernel (light_flat.cuh) */
+typedef struct DnbFlatTuning
+{
+	int budget, endLanes, patience;
+} DnbFlatTuning;
+
 /* the staging arrays one lighting launch stores into: its own, or every replica's */
 typedef struct DnbStagingTargets
 {

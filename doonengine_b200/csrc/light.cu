@@ -24,6 +24,7 @@
  */
 #include "kernels.h"
 #include "trace.cuh"
+#include <stdlib.h>
 
 /* LI:23 */
 __constant__ float c_spherePoints[15][3] = {
@@ -209,13 +210,16 @@ DNB_FN int nth_voxel(const uint32_t* mask, const uint16_t* prefix, uint32_t numV
 /* the three staged words of one voxel -> row `at` of every target array (1 target, or every replica's over NVLink) */
 DNB_FN void stage_words(const DnbStagingTargets& T, size_t at, uint32_t w1, uint32_t w2, uint32_t w3)
 {
-	for(uint32_t p = 0; p < T.count; p++)
-	{
-		uint32_t* out = T.dst[p] + at;
-		out[0] = w1;
-		out[32] = w2;
-		out[64] = w3;
-	}
+	/* static indices (the table lives in the kernel's parameter bank; a dynamic index would copy it to local memory) */
+#pragma unroll
+	for(uint32_t p = 0; p < DNB_MAX_PEERS; p++)
+		if(p < T.count)
+		{
+			uint32_t* out = T.dst[p] + at;
+			out[0] = w1;
+			out[32] = w2;
+			out[64] = w3;
+		}
 }
 
 template <bool COUNT>
@@ -394,18 +398,57 @@ __global__ void dn_merge_visible_peers_kernel(DnbPeerTable T, uint32_t* __restri
 		visible[i] |= add;
 }
 
+#include "light_flat.cuh"
+
+static DnbFlatTuning g_flatTuning = {0, 0, 0};
+
+/* scheduling knobs of the persistent kernel (experiments; results do not depend on them) */
+extern "C" void DN_b200_set_flat_tuning(int budget, int endLanes, int patience)
+{
+	g_flatTuning.budget = budget;
+	g_flatTuning.endLanes = endLanes;
+	g_flatTuning.patience = patience;
+}
+
 extern "C" cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream)
 {
 	return cudaMemcpyToSymbolAsync(c_light, params, sizeof(DnbLightParams), 0, cudaMemcpyHostToDevice, stream);
 }
 
 extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
-                                        const DnbStagingTargets* targets, cudaStream_t stream)
+                                        const DnbStagingTargets* targets, uint32_t* flatCounter, cudaStream_t stream)
 {
 	if(numRequests == 0 || numCtas == 0)
 		return cudaSuccess;
 	if(scene->counters)
 		dn_light_kernel<true><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets);
+	else if(flatCounter)
+	{
+		/* persistent warps: enough CTAs to fill the machine, each lane pulls voxels from the work counter */
+		static int ctasPerDevice = 0;
+		if(ctasPerDevice == 0)
+		{
+			int dev = 0, sms = 148, perSm = 4;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dn_light_flat_kernel, FLAT_WARPS * 32, 0) != cudaSuccess || perSm < 1)
+				perSm = 4;
+			ctasPerDevice = sms * perSm;
+		}
+		cudaError_t e = cudaMemsetAsync(flatCounter, 0, sizeof(uint32_t), stream);
+		if(e != cudaSuccess)
+			return e;
+		const uint32_t grid = numCtas < (uint32_t)ctasPerDevice ? numCtas : (uint32_t)ctasPerDevice;
+		DnbFlatTuning& tuning = g_flatTuning;
+		if(tuning.budget == 0)
+		{
+			auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
+			tuning.budget = knob("DN_B200_FLAT_BUDGET", 12);
+			tuning.endLanes = knob("DN_B200_FLAT_END", 8);
+			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 2);
+		}
+		dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, numCtas * 128u, flatCounter, *targets, tuning);
+	}
 	else
 		dn_light_kernel<false><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets);
 	return cudaGetLastError();

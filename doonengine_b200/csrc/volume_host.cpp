@@ -773,6 +773,28 @@ extern "C" void DN_set_view_projection_matrices(DNvolume* vol, float aspectRatio
 	memcpy(projection->m, P.m, sizeof(P.m));
 }
 
+/* `count` DN_set_compressed_voxel calls in one: voxel positions in VOXEL units (split like DN_separate_position); a voxel whose
+ * material is DN_MATERIAL_EMPTY is removed (DN_remove_voxel).  Positions outside the map are skipped.  Returns the edits applied. */
+extern "C" size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions, const DNcompressedVoxel* voxels)
+{
+	size_t applied = 0;
+	for(size_t i = 0; i < count; i++)
+	{
+		DNivec3 mapPos, chunkPos;
+		if(positions[i].x < 0 || positions[i].y < 0 || positions[i].z < 0)
+			continue;
+		DN_separate_position(positions[i], &mapPos, &chunkPos);
+		if(!DN_in_map_bounds(vol, mapPos))
+			continue;
+		if((voxels[i].normal >> 24) == DN_MATERIAL_EMPTY)
+			DN_remove_voxel(vol, mapPos, chunkPos);
+		else
+			DN_set_compressed_voxel(vol, mapPos, chunkPos, voxels[i]);
+		applied++;
+	}
+	return applied;
+}
+
 extern "C" void DN_b200_touch_tile(DNvolume* vol, DNivec3 mapPos)
 {
 	if(DN_in_map_bounds(vol, mapPos))

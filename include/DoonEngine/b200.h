@@ -35,6 +35,10 @@ bool   DN_b200_read_framebuffer(GLuint fb, float* dst, size_t bytes); /* synchro
 bool   DN_b200_clear_framebuffer(GLuint fb, float value);
 /* asynchronous read-back on a side stream: ordered after the work queued so far, overlaps with what is queued next */
 bool   DN_b200_read_framebuffer_async(GLuint fb, float* dst, size_t bytes);
+/* the rows THIS replica of a sharded volume drew, into a whole-image buffer (e.g. pinned memory shared by the replicas' processes) */
+bool   DN_b200_read_framebuffer_rows_async(GLuint fb, DNvolume* vol, float* dst, size_t bytes);
+bool   DN_b200_host_register(void* ptr, size_t bytes);   /* cudaHostRegister(portable) on caller-owned memory */
+bool   DN_b200_host_unregister(void* ptr);
 bool   DN_b200_wait_framebuffer(void);            /* every read-back queued so far */
 bool   DN_b200_wait_framebuffer_read(GLuint fb);  /* the last read-back of this framebuffer only */
 
@@ -42,6 +46,14 @@ bool   DN_b200_wait_framebuffer_read(GLuint fb);  /* the last read-back of this 
 typedef struct DNb200hit { int32_t status; uint32_t mapIndex, localIndex, recordIndex; } DNb200hit;
 bool DN_b200_capture_hits(GLuint fb, bool enable);
 bool DN_b200_read_hits(GLuint fb, DNb200hit* dst, size_t count);
+
+/* ---- lighting kernel choice: 0 = one warp per lighting request (the reference's work-group shape, voxel.c:950 / LI:3),
+ * 1 = persistent warps running every voxel as a state machine with dynamic work fetch (default; same results bit for bit).
+ * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat". ---- */
+void DN_b200_set_light_kernel(int which);
+int  DN_b200_get_light_kernel(void);
+/* scheduling knobs of the persistent kernel (see csrc/light_flat.cuh); results do not depend on them.  0 = defaults / environment */
+void DN_b200_set_flat_tuning(int budget, int endLanes, int patience);
 
 /* ---- request list ---- */
 /* copies the device-built request list into vol->lightingRequests (growing it like voxel.c:1474-1484); returns the count */
@@ -82,7 +94,10 @@ void DN_b200_enable_timing(bool enable); /* record CUDA events around each kerne
 /* tiles whose host-side state was changed WITHOUT going through a DN_* call (e.g. writing vol->chunks[i].voxels
  * directly and setting .updated) must be announced, because DN_sync_gpu does not scan the whole map */
 void DN_b200_touch_tile(DNvolume* vol, DNivec3 mapPos);
-void DN_b200_rescan(DNvolume* vol); /* marks every tile touched: the next writing sync reconciles the whole map */
+void DN_b200_rescan(DNvolume* vol);
+/* `count` DN_set_compressed_voxel / DN_remove_voxel calls in one (voxel.c:1126-1183): positions in voxel units, a voxel with
+ * material DN_MATERIAL_EMPTY removes; positions outside the map are skipped; returns the number of edits applied */
+size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions, const DNcompressedVoxel* voxels); /* marks every tile touched: the next writing sync reconciles the whole map */
 
 /* ---- multi-GPU: one process per GPU, the same volume replicated in each ---- */
 /* this process lights requests [rank*ceil(R/world), ...) and draws the rank-th band of 16-pixel rows */

@@ -18,6 +18,15 @@ pytestmark = pytest.mark.gpu
 W, H, FRAMES = 320, 192, 4
 
 
+@pytest.fixture(autouse=True, params=["flat", "warp"])
+def light_kernel(request, dn):
+    """every test of this module runs against both lighting kernels: the persistent state machine (light_flat.cuh, the
+    default) and the one-warp-per-request kernel (light.cu); their results must be the same bits."""
+    dn.lib().DN_b200_set_light_kernel(1 if request.param == "flat" else 0)
+    yield request.param
+    dn.lib().DN_b200_set_light_kernel(1)
+
+
 def _compare_state(cuda, ref_state, what, exact_light=False):
     st = records_by_tile(cuda)
     for k in ("tiles", "counts", "masks", "partial", "pos", "samples", "visible"):

@@ -1,0 +1,53 @@
+"""A/B of the lighting kernels and of the persistent kernel's scheduling knobs on one scene (run on the GPU box).
+usage: python tools/light_sweep.py c2|c3s|c5s [frames]"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import doonengine_b200 as dn  # noqa: E402
+import torch  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+scene, tiles, (w, h), desc = bench.CONFIGS[cfg]
+L = dn.lib()
+dn.init(0)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+L.DN_b200_set_stream(stream.cuda_stream)
+chunks, camera = bench.make_chunks(scene, tiles)
+e = bench.build_engine(dn.Engine, scene, tiles, chunks, camera)
+e.sync(dn.DN_WRITE, 1)
+fb = e.framebuffer(w, h)
+view, proj = e.view_projection(h / w)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+variants = [("warp", None)] + [("flat", k) for k in [(24, 28, 16), (24, 32, 16), (24, 28, 32)]]
+out = []
+k = 0
+for name, knobs in variants:
+    L.DN_b200_set_light_kernel(1 if name == "flat" else 0)
+    if knobs:
+        L.DN_b200_set_flat_tuning(*knobs)
+    times = []
+    for f in range(frames + 2):
+        L.DN_draw(e.vol, fb, view, proj, -1, -1)
+        L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
+        flush.fill_(f & 255)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        L.DN_b200_light_compute(e.vol, 1, 1000, bench.frame_time(k))
+        b.record(stream)
+        L.DN_b200_light_commit(e.vol)
+        torch.cuda.synchronize()
+        k += 1
+        if f >= 2:
+            times.append(a.elapsed_time(b))
+    rec = {"config": cfg, "kernel": name, "knobs": knobs, "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "requests": int(e.vol.contents.numLightingRequests)}
+    print(json.dumps(rec), flush=True)
+    out.append(rec)

@@ -18,8 +18,10 @@ for r in rows:
     if r[0] == "Kernel Name":
         launches += 1
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
+        continue
+    if r[0] == "Function Name":
         continue
     if r[0] == "Line No":
         hdr = r
