@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdoon_b200.so")
+LIB_PATH = os.environ.get("DN_B200_LIB") or os.path.join(HERE, "libdoon_b200.so")  # $DN_B200_LIB: an experimental build variant
 
 
 # ---- C structs (include/DoonEngine/*.h) ----
@@ -79,7 +79,8 @@ class DNb200stats(C.Structure):
                 ("residentChunks", C.c_uint64), ("residentRecords", C.c_uint64),
                 ("slotCap", C.c_uint64), ("recordCap", C.c_uint64), ("voxelsLit", C.c_uint64),
                 ("lastDrawMs", C.c_float), ("lastCompactMs", C.c_float), ("lastUploadMs", C.c_float),
-                ("lastLightMs", C.c_float), ("lastCommitMs", C.c_float)]
+                ("lastLightMs", C.c_float), ("lastCommitMs", C.c_float),
+                ("lightLaunchesWarp", C.c_uint64), ("lightLaunchesFlat", C.c_uint64), ("nsPerCtaWarp", C.c_float), ("nsPerCtaFlat", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -46,8 +46,12 @@ def up_to_date():
     return all(os.path.getmtime(f) <= t for f in _inputs())
 
 
-def build(force=False, verbose=False):
-    """compile (if stale) and return the path of the shared library."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """compile (if stale) and return the path of the shared library.  `defines` / `out` build an experimental variant
+    (e.g. defines=["FLAT_FIRST_STEP=1"], out="libdoon_b200_v1.so"; load it with $DN_B200_LIB)."""
+    global LIB
+    if out:
+        return _build_variant(defines, out, verbose)
     if not force and up_to_date():
         return LIB
     objdir = os.path.join(HERE, "build")
@@ -75,6 +79,27 @@ def build(force=False, verbose=False):
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return LIB
+
+
+def _build_variant(defines, out, verbose):
+    objdir = os.path.join(HERE, "build", os.path.splitext(out)[0])
+    os.makedirs(objdir, exist_ok=True)
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    objs, procs = [], []
+    for s in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
+        objs.append(obj)
+        cmd = [nvcc()] + NVCC_FLAGS + inc + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stdout.write(o)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed")
+    path = os.path.join(HERE, out)
+    subprocess.check_call([nvcc()] + ARCH + ["-shared", "-o", path] + objs + ["-Xcompiler", "-pthread", "-cudart", "static"])
+    return path
 
 
 if __name__ == "__main__":

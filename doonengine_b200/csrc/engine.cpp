@@ -133,6 +133,13 @@ void device_destroy(VolumeImpl* v)
 	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->blob); device_free(v->litCounter);
 	device_free(v->mailbox); device_free(v->barrierStatus);
 	v->peerAttached = false;
+	for(int slot = 0; slot < 2; slot++)
+	{
+		if(v->tuner.begin[slot]) cudaEventDestroy(v->tuner.begin[slot]);
+		if(v->tuner.end[slot]) cudaEventDestroy(v->tuner.end[slot]);
+		v->tuner.begin[slot] = v->tuner.end[slot] = nullptr;
+		v->tuner.slotKernel[slot] = -1;
+	}
 	if(v->pinnedBlob) cudaFreeHost(v->pinnedBlob);
 	if(v->pinnedScalars) cudaFreeHost(v->pinnedScalars);
 	if(v->counters) cudaFree(v->counters);
@@ -1021,21 +1028,80 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 	}
 }
 
-/* which lighting kernel runs: 0 = one warp per request (light.cu), 1 = persistent state machine (light_flat.cuh).
- * Default from $DN_B200_LIGHT_KERNEL ("warp" / "flat"), overridden by DN_b200_set_light_kernel. */
+/* which lighting kernel runs: 0 = one warp per request (light.cu), 1 = persistent state machine (light_flat.cuh), 2 = whichever
+ * is faster on this volume (default).  Initial value from $DN_B200_LIGHT_KERNEL ("warp" / "flat" / "auto"), overridden by
+ * DN_b200_set_light_kernel. */
 static int g_lightKernel = -1;
 static int light_kernel_choice()
 {
 	if(g_lightKernel < 0)
 	{
 		const char* env = getenv("DN_B200_LIGHT_KERNEL");
-		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : 1;
+		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : (env && strcmp(env, "flat") == 0) ? 1 : 2;
 	}
 	return g_lightKernel;
 }
 
-extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = which ? 1 : 0; }
+extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = (which >= 0 && which <= 2) ? which : 2; }
 extern "C" int DN_b200_get_light_kernel(void) { return light_kernel_choice(); }
+
+/* Auto mode.  The two kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a
+ * question of speed, and that depends on the scene: short rays that end together favour one warp per request, rays of very
+ * different length favour the persistent state machine (2.6x on the sparse map).  Every dispatch is bracketed by two events
+ * (no synchronisation: they are read one or two dispatches later, once they have completed anyway); the first dispatches
+ * alternate between the kernels (the very first one, the jitter-free first sample, is not representative and is not used),
+ * then the faster one runs, and the other is re-timed every 64th dispatch in case the camera or the map has changed. */
+static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, int* slotOut)
+{
+	VolumeImpl::LightTuner& t = v->tuner;
+	*slotOut = -1;
+	const int mode = light_kernel_choice();
+	if(mode != 2)
+		return mode;
+
+	/* harvest finished timings */
+	for(int slot = 0; slot < 2; slot++)
+	{
+		if(t.slotKernel[slot] < 0 || cudaEventQuery(t.end[slot]) != cudaSuccess)
+			continue;
+		float ms = 0.0f;
+		if(cudaEventElapsedTime(&ms, t.begin[slot], t.end[slot]) == cudaSuccess && t.slotCtas[slot] > 0)
+		{
+			const int k = t.slotKernel[slot];
+			const double ns = 1e6 * (double)ms / (double)t.slotCtas[slot];
+			t.nsPerCta[k] = t.samples[k] == 0 ? ns : 0.5 * t.nsPerCta[k] + 0.5 * ns;
+			t.samples[k]++;
+		}
+		t.slotKernel[slot] = -1;
+	}
+	cudaGetLastError(); /* cudaErrorNotReady from the queries above is not an error */
+
+	int k;
+	const uint64_t n = t.dispatches++;
+	if(t.samples[0] < 2 || t.samples[1] < 2)
+		k = (int)(n & 1u) ^ 1;                     /* flat, warp, flat, warp ... until both have two timings */
+	else
+	{
+		k = t.nsPerCta[1] <= t.nsPerCta[0] ? 1 : 0;
+		if((n & 63u) == 63u)
+			k ^= 1;                                  /* keep the loser's estimate fresh */
+	}
+
+	/* time this dispatch if a slot is free (never the first dispatch of a volume) */
+	if(n > 0 && numCtas > 0)
+		for(int slot = 0; slot < 2; slot++)
+			if(t.slotKernel[slot] < 0)
+			{
+				if(!t.begin[slot] && (cudaEventCreate(&t.begin[slot]) != cudaSuccess || cudaEventCreate(&t.end[slot]) != cudaSuccess))
+					break;
+				t.slotKernel[slot] = k;
+				t.slotCtas[slot] = numCtas;
+				cudaEventRecord(t.begin[slot], s);
+				*slotOut = slot;
+				break;
+			}
+	return k;
+}
 
 static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSamples, float time)
 {
@@ -1141,7 +1207,12 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
 	/* a slice that is not the last one ends on a CTA boundary (slice_len is a multiple of 4); the last CTA of the list is cut by numRequests */
 	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
-	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, light_kernel_choice() == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
+	int timingSlot = -1;
+	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
+	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
+	if(timingSlot >= 0)
+		cudaEventRecord(v->tuner.end[timingSlot], s);
+	v->tuner.launches[kernel]++;
 	return ok;
 }
 
@@ -1331,6 +1402,10 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 	VolumeImpl* v = impl_of(vol);
 	v->stats.slotCap = v->slots.cap;
 	v->stats.recordCap = v->records.cap;
+	v->stats.lightLaunchesWarp = v->tuner.launches[0];
+	v->stats.lightLaunchesFlat = v->tuner.launches[1];
+	v->stats.nsPerCtaWarp = (float)v->tuner.nsPerCta[0];
+	v->stats.nsPerCtaFlat = (float)v->tuner.nsPerCta[1];
 	if(ctx().ready && v->litCounter.ptr && DN_b200_synchronize())
 	{
 		unsigned long long lit = 0;

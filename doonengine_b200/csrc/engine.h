@@ -99,6 +99,19 @@ struct VolumeImpl
 	size_t stagedRequests = 0;                 /* requests covered by the staging array (last compute phase) */
 	int    shardRank = 0, shardWorld = 1;
 
+	/* ---- lighting-kernel selection (engine.cpp pick_light_kernel): both kernels give the same bits, so the faster one for
+	 * THIS map and camera is found by timing them on live dispatches ---- */
+	struct LightTuner
+	{
+		cudaEvent_t begin[2] = {nullptr, nullptr}, end[2] = {nullptr, nullptr}; /* two timing slots in rotation */
+		int      slotKernel[2] = {-1, -1};   /* kernel timed in each slot, -1 = slot free */
+		uint32_t slotCtas[2] = {0, 0};
+		double   nsPerCta[2] = {0.0, 0.0};    /* running estimate per kernel */
+		uint32_t samples[2] = {0, 0};
+		uint64_t dispatches = 0;
+		uint64_t launches[2] = {0, 0};
+	} tuner;
+
 	/* ---- multi-GPU over peer memory (DoonEngine/b200.h) ---- */
 	bool         peerAttached = false;
 	int          peerMode = 0;              /* DNb200peerMode */

@@ -443,9 +443,9 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 		if(tuning.budget == 0)
 		{
 			auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
-			tuning.budget = knob("DN_B200_FLAT_BUDGET", 12);
-			tuning.endLanes = knob("DN_B200_FLAT_END", 8);
-			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 2);
+			tuning.budget = knob("DN_B200_FLAT_BUDGET", 24);
+			tuning.endLanes = knob("DN_B200_FLAT_END", 28);
+			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 16);
 		}
 		dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, numCtas * 128u, flatCounter, *targets, tuning);
 	}

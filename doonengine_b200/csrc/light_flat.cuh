@@ -13,11 +13,19 @@
  *            ray), start the next ray, or store the voxel's result ...
  *     FETCH  ... and take the next voxel from a global work counter (persistent warps, dynamic fetch)
  *
- * Each trip round the warp's loop counts the lanes per state and runs ONE phase -- the one most lanes are waiting for --
- * for as long as it keeps most of them busy.  A lane that finishes early is not idle until the warp's slowest ray
- * ends; it waits only until enough other lanes want the same phase.  Nothing about a voxel's own sequence of
- * operations changes, so the staged words are bit-identical to dn_light_kernel's (tests/test_parity_gpu.py runs every
- * lighting test against both kernels).
+ * Each trip round the warp's loop counts the lanes per state and runs ONE phase:
+ *   serve   (END / FETCH lanes) once `endLanes` lanes wait for it, or nothing else can run, or the waiting lanes have sat
+ *           through `patience` stepping iterations: ray set-up and shading is by far the most expensive phase, so it should
+ *           run with as many lanes as possible, but a few very long rays must not hold everybody up;
+ *   TILE or VOX burst   the stepping phase with more lanes, until fewer than 3/4 of its lanes are still stepping.
+ * A lane that finishes early is not idle until the warp's slowest ray ends; it waits only until enough other lanes want
+ * the same phase.  Nothing about a voxel's own sequence of operations changes, so the staged words are bit-identical to
+ * dn_light_kernel's (tests/test_parity_gpu.py runs every lighting test against both kernels).
+ *
+ * Measured (B200, profiles/r1_light_kernels.md): 2.6x faster than dn_light_kernel on the sparse map and 2.5x on the bundled
+ * demo map, where ray lengths inside a warp differ wildly; 1.4x SLOWER on the terrain map, whose rays are a handful of steps
+ * long and end together (there the state machine's bookkeeping and the fragmented voxel set-up outweigh the better lane use).
+ * The host therefore times both on live dispatches and runs the faster one (engine.cpp pick_light_kernel).
  *
  * The ray-persistent state of one shader invocation (lastVoxID / lastVoxRefract / voxel, SH:321-325) is per lane and
  * reset per voxel, as one invocation lights one voxel.  Lighting never refracts (LI:209), so the chunk-level DDA shares

@@ -48,8 +48,9 @@ bool DN_b200_capture_hits(GLuint fb, bool enable);
 bool DN_b200_read_hits(GLuint fb, DNb200hit* dst, size_t count);
 
 /* ---- lighting kernel choice: 0 = one warp per lighting request (the reference's work-group shape, voxel.c:950 / LI:3),
- * 1 = persistent warps running every voxel as a state machine with dynamic work fetch (default; same results bit for bit).
- * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat". ---- */
+ * 1 = persistent warps running every voxel as a state machine with dynamic work fetch (same results bit for bit),
+ * 2 = auto (default): both are timed on live dispatches of this volume and the faster one runs.
+ * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat" | "auto". ---- */
 void DN_b200_set_light_kernel(int which);
 int  DN_b200_get_light_kernel(void);
 /* scheduling knobs of the persistent kernel (see csrc/light_flat.cuh); results do not depend on them.  0 = defaults / environment */
@@ -87,6 +88,8 @@ typedef struct DNb200stats
 	uint64_t slotCap, recordCap;
 	uint64_t voxelsLit;                                     /* voxel lighting updates committed since creation */
 	float    lastDrawMs, lastCompactMs, lastUploadMs, lastLightMs, lastCommitMs; /* device time of the last call of each kind, when timing is on */
+	uint64_t lightLaunchesWarp, lightLaunchesFlat;          /* lighting dispatches run by each kernel */
+	float    nsPerCtaWarp, nsPerCtaFlat;                    /* auto mode: running estimate of each kernel's time per 4 requests */
 } DNb200stats;
 void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
 void DN_b200_enable_timing(bool enable); /* record CUDA events around each kernel group (adds a sync when read) */

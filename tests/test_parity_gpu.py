@@ -24,7 +24,7 @@ def light_kernel(request, dn):
     default) and the one-warp-per-request kernel (light.cu); their results must be the same bits."""
     dn.lib().DN_b200_set_light_kernel(1 if request.param == "flat" else 0)
     yield request.param
-    dn.lib().DN_b200_set_light_kernel(1)
+    dn.lib().DN_b200_set_light_kernel(2)  # back to auto
 
 
 def _compare_state(cuda, ref_state, what, exact_light=False):

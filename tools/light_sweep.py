@@ -20,14 +20,14 @@ dn.init(0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 L.DN_b200_set_stream(stream.cuda_stream)
-chunks, camera = bench.make_chunks(scene, tiles)
+chunks, camera = bench.make_chunks(scene, tiles) if scene != "demo" else ([], {})
 e = bench.build_engine(dn.Engine, scene, tiles, chunks, camera)
 e.sync(dn.DN_WRITE, 1)
 fb = e.framebuffer(w, h)
 view, proj = e.view_projection(h / w)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-variants = [("warp", None)] + [("flat", k) for k in [(24, 28, 16), (24, 32, 16), (24, 28, 32)]]
+variants = [("warp", None)] + [("flat", k) for k in [(24, 28, 16), (24, 32, 16), (24, 16, 16)]]
 out = []
 k = 0
 for name, knobs in variants:
