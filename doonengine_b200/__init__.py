@@ -181,6 +181,7 @@ _PROTOTYPES = {
     "DN_b200_enable_timing": (None, [C.c_bool]),
     "DN_b200_touch_tile": (None, [C.POINTER(DNvolume), DNivec3]),
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
+    "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
     "DN_b200_set_shard": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int]),
     "DN_b200_light_compute": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int, C.c_float]),
@@ -371,6 +372,14 @@ class Engine:
         v = np.ascontiguousarray(voxels, dtype=np.uint32)
         assert p.ndim == 2 and p.shape[1] == 3 and v.shape == (p.shape[0], 2)
         return int(self.L.DN_b200_set_voxels(self.vol, p.shape[0], p.ctypes.data, v.ctypes.data))
+
+    def pack_chunk(self, map_pos):
+        """(slot header as SLOT_DT scalar, records uint32 [n,4]) of the chunk at map_pos as the next writing sync would upload it;
+        host-only.  None if the tile has no chunk."""
+        slot = np.zeros(1, SLOT_DT)
+        rec = np.zeros((512, 4), np.uint32)
+        n = self.L.DN_b200_pack_chunk(self.vol, DNivec3(*map_pos), slot.ctypes.data, rec.ctypes.data)
+        return None if n < 0 else (slot[0], rec[:n].copy())
 
     def compress_voxel(self, material, normal, albedo):
         r = self.L.DN_compress_voxel(DNvoxel(material, DNvec3(*normal), DNcolor(*albedo)))

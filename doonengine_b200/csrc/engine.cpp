@@ -11,6 +11,9 @@
 #include "hostmath.h"
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -200,41 +203,104 @@ struct ScopedTimer
 /* ------------------------------------------------------------------------------------------------ */
 /* chunk packing: voxel.c:1391-1461                                                                   */
 
-static inline bool face_open(const DNvolume* vol, const DNchunk* c, int x, int y, int z)
+/* sRGB -> linear, truncated, with the reference's constants and libm powf (voxel.c:1441-1447); host-only, no CUDA needed */
+static const uint8_t* albedo_lut()
 {
-	if((unsigned)x >= 8u || (unsigned)y >= 8u || (unsigned)z >= 8u)
-		return true; /* culling is chunk-local: border voxels are always kept */
-	const uint32_t mat = c->voxels[x][y][z].normal >> 24;
-	return mat == DN_MATERIAL_EMPTY || vol->materials[mat].opacity < 1.0f;
+	static uint8_t lut[256];
+	static bool ready = false;
+	if(!ready)
+	{
+		for(int i = 0; i < 256; i++)
+		{
+			float f = (float)i * 0.00392156862f;
+			f = powf(f, DN_GAMMA);
+			f = f * 255.0f;
+			lut[i] = (uint8_t)f;
+		}
+		ready = true;
+	}
+	return lut;
 }
 
-/* fills the slot header (everything but voxelBase) and the records in local-index order; returns the record count */
-static uint32_t pack_chunk(const DNvolume* vol, const DNchunk* c, uint32_t mapIndex, DnbSlot* slot, uint4* records)
+/* per material: does a voxel of it hide the faces it touches?  (voxel.c:1391-1394: a face is open when the neighbour is empty or
+ * its material has opacity < 1; NaN compares false, i.e. hides, exactly as upstream) */
+static void opaque_table(const DNvolume* vol, uint8_t out[256])
 {
-	const uint8_t* lut = ctx().albedoLut;
+	for(int m = 0; m < 256; m++)
+		out[m] = (m != DN_MATERIAL_EMPTY && !(vol->materials[m].opacity < 1.0f)) ? 1 : 0;
+}
+
+/* transpose of an 8x8 bit matrix held as 8 bytes (byte i, bit j  <->  byte j, bit i) */
+static inline uint64_t transpose8(uint64_t x)
+{
+	uint64_t t;
+	t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;  x = x ^ t ^ (t << 7);
+	t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+	t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+	return x;
+}
+
+/* fills the slot header (everything but voxelBase) and the records in local-index order; returns the record count.
+ * Same result as _DN_chunk_to_gpu + _DN_check_face_visible (voxel.c:1391-1461) voxel by voxel, computed on bit rows: the chunk
+ * is stored [x][y][z], so the 8 voxels of an (x, y) row are one cache line; each row becomes two bytes (solid, opaque) and the
+ * six-neighbour test becomes a handful of ANDs per row instead of six dependent loads per voxel. */
+static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const DNchunk* c, uint32_t mapIndex, DnbSlot* slot, uint4* records)
+{
+	const uint8_t* lut = albedo_lut();
 	memset(slot, 0, sizeof(*slot));
 	slot->mapIndex = mapIndex;
 	slot->pos[0] = c->pos.x; slot->pos[1] = c->pos.y; slot->pos[2] = c->pos.z;
 	slot->numSamples = 0; /* an edit restarts the accumulation (voxel.c:1401) */
 
-	uint32_t n = 0;
-	for(int z = 0; z < 8; z++)
+	/* bit z of S[x][y] / O[x][y]: voxel (x, y, z) is solid / hides its neighbours' faces */
+	uint8_t S[8][8], O[10][10];
+	memset(O, 0, sizeof(O)); /* O is padded by one row on each side; padding = "open" */
+	for(int x = 0; x < 8; x++)
 		for(int y = 0; y < 8; y++)
 		{
-			const uint32_t rowIndex = (uint32_t)(8 * (y + 8 * z));
-			if((rowIndex & 31u) == 0)
-				slot->prefix[rowIndex >> 5] = (uint16_t)n;
-			for(int x = 0; x < 8; x++)
+			unsigned sBits = 0, oBits = 0;
+			for(int z = 0; z < 8; z++)
 			{
-				const DNcompressedVoxel vx = c->voxels[x][y][z];
-				if((vx.normal >> 24) == DN_MATERIAL_EMPTY)
-					continue;
-				if(!(face_open(vol, c, x + 1, y, z) || face_open(vol, c, x - 1, y, z) || face_open(vol, c, x, y + 1, z) ||
-				     face_open(vol, c, x, y - 1, z) || face_open(vol, c, x, y, z + 1) || face_open(vol, c, x, y, z - 1)))
-					continue;
+				const uint32_t mat = c->voxels[x][y][z].normal >> 24;
+				sBits |= (unsigned)(mat != DN_MATERIAL_EMPTY) << z;
+				oBits |= (unsigned)opaque[mat] << z;
+			}
+			S[x][y] = (uint8_t)sBits;
+			O[x + 1][y + 1] = (uint8_t)oBits;
+		}
 
-				const uint32_t index = rowIndex + (uint32_t)x;
-				slot->mask[index >> 5] |= 1u << (index & 31u);
+	/* surface voxels, regrouped: byte z of T[y] holds bits x (a row of the local-index order x + 8*(y + 8*z)) */
+	uint64_t T[8];
+	for(int y = 0; y < 8; y++)
+	{
+		uint64_t rows = 0; /* byte x = surface bits over z of row (x, y) */
+		for(int x = 0; x < 8; x++)
+		{
+			const unsigned o = O[x + 1][y + 1];
+			/* hidden: both z neighbours inside the chunk and opaque, and the four x / y neighbours (padding rows are 0 = open) */
+			const unsigned hidden = (o >> 1) & (o << 1) & 0x7Eu & O[x][y + 1] & O[x + 2][y + 1] & O[x + 1][y] & O[x + 1][y + 2];
+			rows |= (uint64_t)(S[x][y] & ~hidden & 0xFFu) << (8 * x);
+		}
+		T[y] = transpose8(rows);
+	}
+
+	uint32_t n = 0;
+	for(int z = 0; z < 8; z++)
+		for(int q = 0; q < 2; q++)
+		{
+			/* mask word 2z + q: rows y = 4q .. 4q+3 of layer z */
+			uint32_t word = 0;
+			for(int k = 0; k < 4; k++)
+				word |= (uint32_t)((T[4 * q + k] >> (8 * z)) & 0xFFu) << (8 * k);
+			const int w = 2 * z + q;
+			slot->mask[w] = word;
+			slot->prefix[w] = (uint16_t)n;
+			while(word)
+			{
+				const int bit = __builtin_ctz(word);
+				word &= word - 1;
+				const int x = bit & 7, y = 4 * q + (bit >> 3);
+				const DNcompressedVoxel vx = c->voxels[x][y][z];
 				uint4 rec;
 				rec.x = vx.normal;
 				rec.y = ((uint32_t)lut[vx.albedo >> 24] << 24) | ((uint32_t)lut[(vx.albedo >> 16) & 0xFF] << 16) | ((uint32_t)lut[(vx.albedo >> 8) & 0xFF] << 8);
@@ -246,6 +312,109 @@ static uint32_t pack_chunk(const DNvolume* vol, const DNchunk* c, uint32_t mapIn
 	slot->numVoxels = n;
 	return n;
 }
+
+} // namespace dnb
+
+/* host-only (no CUDA): packs the chunk at mapPos exactly as the next writing sync would upload it -- 128-byte slot header
+ * (voxelBase = 0) and up to 512 records -- for tests and offline tools.  Returns the record count, -1 if the tile has no chunk. */
+extern "C" int DN_b200_pack_chunk(DNvolume* vol, DNivec3 mapPos, void* slotOut128, void* recordsOut)
+{
+	if(!DN_in_map_bounds(vol, mapPos))
+		return -1;
+	const size_t mapIndex = DN_FLATTEN_INDEX(mapPos, vol->mapSize);
+	if(vol->map[mapIndex].flag == 0)
+		return -1;
+	uint8_t opaque[256];
+	dnb::opaque_table(vol, opaque);
+	return (int)dnb::pack_chunk(vol, opaque, &vol->chunks[vol->map[mapIndex].chunkIndex], (uint32_t)mapIndex, (DnbSlot*)slotOut128, (uint4*)recordsOut);
+}
+
+namespace dnb
+{
+
+/* persistent host workers for packing: spawning threads every sync costs more than packing a small batch */
+class PackPool
+{
+public:
+	static PackPool& get()
+	{
+		static PackPool pool;
+		return pool;
+	}
+	unsigned size() const { return (unsigned)threads.size() + 1; }
+	/* runs fn(t) for t in [0, n) on the pool (the caller takes part); n <= size() */
+	void run(unsigned n, const std::function<void(unsigned)>& fn)
+	{
+		if(n <= 1)
+		{
+			fn(0);
+			return;
+		}
+		{
+			std::unique_lock<std::mutex> lock(m);
+			job = &fn;
+			jobCount = n;
+			nextIndex = 1;
+			pending = n - 1;
+			generation++;
+		}
+		wake.notify_all();
+		fn(0);
+		std::unique_lock<std::mutex> lock(m);
+		done.wait(lock, [&] { return pending == 0; });
+		job = nullptr;
+	}
+
+private:
+	PackPool()
+	{
+		unsigned n = std::thread::hardware_concurrency();
+		if(n == 0) n = 4;
+		n = std::min(n, 32u);
+		for(unsigned i = 1; i < n; i++)
+			threads.emplace_back([this] { loop(); });
+	}
+	~PackPool()
+	{
+		{
+			std::unique_lock<std::mutex> lock(m);
+			quit = true;
+		}
+		wake.notify_all();
+		for(auto& t : threads)
+			t.join();
+	}
+	void loop()
+	{
+		uint64_t seen = 0;
+		for(;;)
+		{
+			unsigned index;
+			const std::function<void(unsigned)>* fn;
+			{
+				std::unique_lock<std::mutex> lock(m);
+				wake.wait(lock, [&] { return quit || (generation != seen && nextIndex < jobCount); });
+				if(quit)
+					return;
+				index = nextIndex++;
+				if(nextIndex >= jobCount)
+					seen = generation;
+				fn = job;
+			}
+			(*fn)(index);
+			std::unique_lock<std::mutex> lock(m);
+			if(--pending == 0)
+				done.notify_one();
+		}
+	}
+	std::vector<std::thread> threads;
+	std::mutex m;
+	std::condition_variable wake, done;
+	const std::function<void(unsigned)>* job = nullptr;
+	unsigned jobCount = 0, nextIndex = 0, pending = 0;
+	uint64_t generation = 0;
+	bool quit = false;
+};
 
 /* ---- record-pool allocator: power-of-two nodes of 16..512 records, per-class free lists over a bump pointer ---- */
 static inline int node_class(uint32_t n)
@@ -356,15 +525,11 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 	uint4* hRecords = reinterpret_cast<uint4*>(v->pinnedBlob + offRecords);
 
 	/* parallel pack: worker t owns a contiguous range of items and packs their records back to back into its arena */
+	uint8_t opaque[256];
+	opaque_table(vol, opaque);
 	unsigned workers = 1;
-	if(count >= 256)
-	{
-		workers = std::thread::hardware_concurrency();
-		if(workers == 0) workers = 4;
-		workers = std::min<unsigned>(workers, 32);
-		workers = std::min<unsigned>(workers, (unsigned)(count / 64));
-		if(workers == 0) workers = 1;
-	}
+	if(count >= 128)
+		workers = std::max(1u, std::min<unsigned>(PackPool::get().size(), (unsigned)(count / 64)));
 	std::vector<size_t> arenaUsed(workers, 0);
 	auto work = [&](unsigned t)
 	{
@@ -381,21 +546,11 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 				memset(&hHeaders[i], 0, sizeof(DnbSlot));
 				continue;
 			}
-			cursor += pack_chunk(vol, &vol->chunks[items[i].chunkIndex], items[i].tile, &hHeaders[i], hRecords + cursor);
+			cursor += pack_chunk(vol, opaque, &vol->chunks[items[i].chunkIndex], items[i].tile, &hHeaders[i], hRecords + cursor);
 		}
 		arenaUsed[t] = cursor - begin * 512;
 	};
-	if(workers == 1)
-		work(0);
-	else
-	{
-		std::vector<std::thread> pool;
-		for(unsigned t = 1; t < workers; t++)
-			pool.emplace_back(work, t);
-		work(0);
-		for(auto& th : pool)
-			th.join();
-	}
+	PackPool::get().run(workers, work);
 
 	/* serial: slots and record nodes */
 	size_t recordBytes = 0;
@@ -652,15 +807,6 @@ extern "C" bool DN_init(void)
 	{
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_FATAL, "failed to create CUDA streams");
 		return false;
-	}
-
-	/* sRGB -> linear, truncated, with the reference's constants and libm powf (voxel.c:1441-1447) */
-	for(int i = 0; i < 256; i++)
-	{
-		float f = (float)i * 0.00392156862f;
-		f = powf(f, DN_GAMMA);
-		f = f * 255.0f;
-		c.albedoLut[i] = (uint8_t)f;
 	}
 
 	c.framebuffers.clear();

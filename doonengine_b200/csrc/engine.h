@@ -45,7 +45,6 @@ struct Context
 	cudaEvent_t  evUploadDone = nullptr, evComputeDone = nullptr;
 	cudaEvent_t  evT0 = nullptr, evT1 = nullptr;
 	bool         timing = false;
-	uint8_t      albedoLut[256];         /* trunc(255 * (a * 0.00392156862)^2.2), voxel.c:1441-1447 */
 	std::vector<Framebuffer> framebuffers;
 
 	cudaStream_t stream() const { return useUserStream ? userStream : ownStream; }

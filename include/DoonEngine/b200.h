@@ -98,6 +98,10 @@ void DN_b200_enable_timing(bool enable); /* record CUDA events around each kerne
  * directly and setting .updated) must be announced, because DN_sync_gpu does not scan the whole map */
 void DN_b200_touch_tile(DNvolume* vol, DNivec3 mapPos);
 void DN_b200_rescan(DNvolume* vol);
+/* host-only (works without a CUDA device): packs the chunk at mapPos exactly as the next writing sync would upload it (surface
+ * culling, bit mask, prefix counts, albedo linearisation: voxel.c:1391-1461) into a 128-byte slot header (csrc/layout.h DnbSlot,
+ * voxelBase = 0) and up to 512 16-byte records; returns the record count, -1 if the tile has no chunk */
+int DN_b200_pack_chunk(DNvolume* vol, DNivec3 mapPos, void* slotOut128, void* recordsOut);
 /* `count` DN_set_compressed_voxel / DN_remove_voxel calls in one (voxel.c:1126-1183): positions in voxel units, a voxel with
  * material DN_MATERIAL_EMPTY removes; positions outside the map are skipped; returns the number of edits applied */
 size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions, const DNcompressedVoxel* voxels); /* marks every tile touched: the next writing sync reconciles the whole map */

@@ -156,3 +156,73 @@ def test_set_map_size_keeps_overlap(dn):
     assert not L.DN_in_map_bounds(vol, dn.DNivec3(3, 0, 3))
     assert int((e.host_chunks()["pos"][:, 0] >= 0).sum()) == 1  # the chunk outside the new box was dropped
     e.close()
+
+
+def test_host_packing_matches_oracle(oracle_mod):
+    """the product's chunk packing (surface culling on bit rows, mask, prefix counts, albedo linearisation; csrc/engine.cpp
+    pack_chunk, host-only entry DN_b200_pack_chunk) against the oracle's restatement of voxel.c:1391-1461, chunk by chunk, on the
+    bundled demo map, the all-materials scene (glass exposes its neighbours) and random chunks of every density."""
+    import doonengine_b200 as dn
+    from doonengine_b200 import scenes
+    from conftest import DEMO
+
+    def compare(prod, orc, what):
+        orc.sync(1, 1)
+        st = orc.export_state()
+        sx, sy, _ = prod.map_size
+        assert len(st) > 0
+        for tile, (state, _, hdr, recs) in st.items():
+            pos = (tile % sx, (tile // sx) % sy, tile // (sx * sy))
+            got = prod.pack_chunk(pos)
+            assert got is not None, "%s: tile %d has no chunk in the product" % (what, tile)
+            slot, grec = got
+            assert tuple(int(x) for x in slot["pos"]) == hdr[0]
+            assert tuple(int(x) for x in slot["mask"]) == hdr[3], "%s: surface mask of tile %d" % (what, tile)
+            assert (int(slot["prefix"][4]), int(slot["prefix"][8]), int(slot["prefix"][12])) == hdr[2]
+            assert int(slot["numVoxels"]) == len(recs) and int(slot["numSamples"]) == 0
+            # per-word prefix counts are the running popcount of the mask
+            run = 0
+            for w in range(16):
+                assert int(slot["prefix"][w]) == run
+                run += bin(int(slot["mask"][w])).count("1")
+            assert np.array_equal(grec, np.asarray(recs, dtype=np.uint32)), "%s: records of tile %d" % (what, tile)
+        return len(st)
+
+    # bundled demo map
+    p = dn.Engine(voxvol=DEMO, min_chunks=256, host_only=True)
+    o = oracle_mod.OracleEngine(voxvol=DEMO, min_chunks=256)
+    assert compare(p, o, "demo") == 240
+    p.close(); o.close()
+
+    # every material kind
+    tiles = (6, 4, 6)
+    p = dn.Engine(map_size=tiles, min_chunks=64, host_only=True)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    for e in (p, o):
+        scenes.build(e, scenes.mixed_materials(tiles), **scenes.mixed_camera(tiles))
+    compare(p, o, "mixed")
+    p.close(); o.close()
+
+    # random chunks: densities from almost empty to full, random materials (4 = glass, opacity 0.5)
+    rng = np.random.RandomState(11)
+    tiles = (4, 4, 4)
+    p = dn.Engine(map_size=tiles, min_chunks=64, host_only=True)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    mats = scenes.default_materials()
+    for e in (p, o):
+        e.materials()[:] = mats
+    k = 0
+    for z in range(4):
+        for y in range(4):
+            for x in range(4):
+                density = (k + 1) / 64.0
+                k += 1
+                vox = np.zeros((8, 8, 8, 2), np.uint32)
+                solid = rng.rand(8, 8, 8) < density
+                mat = rng.choice([0, 1, 2, 3, 4], size=(8, 8, 8)).astype(np.uint32)
+                vox[..., 0] = np.where(solid, (mat << 24) | rng.randint(0, 1 << 24, (8, 8, 8)).astype(np.uint32), 0xFFFFFFFF)
+                vox[..., 1] = rng.randint(0, 1 << 32, (8, 8, 8), dtype=np.uint64).astype(np.uint32) & 0xFFFFFF00
+                for e in (p, o):
+                    e.set_chunk((x, y, z), vox)
+    compare(p, o, "random")
+    p.close(); o.close()

@@ -1,11 +1,15 @@
 #!/bin/bash
-# ncu session on the GPU box (run under gpurun): launch list of one bench command + full captures of the two hot kernels.
-# usage: bash tools/profile_gpu.sh [tag] [config]
+# ncu session on the GPU box (run under gpurun): launch list of one bench command + full captures of the hot kernels.
+# usage: bash tools/profile_gpu.sh [tag]
 TAG=${1:-r1}
-CFG=${2:-c2}
 mkdir -p gpurun_out
-CMD="python bench.py --config $CFG --steps 2 --warmup 3 --no-cpu-baseline"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:dn_light_kernel -s 4 -c 2 -f -o gpurun_out/${TAG}_light $CMD > gpurun_out/${TAG}_light.log 2>&1
+CMD="python bench.py --config c2 --steps 2 --warmup 3 --no-cpu-baseline --sampler-ms 0"
+# every launch of the default bench command with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_launches.log 2>&1
+# full captures: the warp-per-request lighting kernel and the draw kernel on config 2, the persistent lighting kernel on the sparse map
+ncu --set full --clock-control none --import-source on -k regex:dn_light_kernel -s 4 -c 2 -f -o gpurun_out/${TAG}_light_warp $CMD --light-kernel warp > gpurun_out/${TAG}_light_warp.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:dn_draw_kernel -s 4 -c 2 -f -o gpurun_out/${TAG}_draw $CMD > gpurun_out/${TAG}_draw.log 2>&1
-ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:dn_light_flat -s 4 -c 1 -f -o gpurun_out/${TAG}_light_flat_c3s python bench.py --config c3s --steps 1 --warmup 3 --no-cpu-baseline --sampler-ms 0 --light-kernel flat > gpurun_out/${TAG}_light_flat_c3s.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:dn_commit -s 4 -c 1 -f -o gpurun_out/${TAG}_commit $CMD > gpurun_out/${TAG}_commit.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:dn_compact -s 8 -c 2 -f -o gpurun_out/${TAG}_compact $CMD > gpurun_out/${TAG}_compact.log 2>&1
+ls -la gpurun_out/ | grep ${TAG}
