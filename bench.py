@@ -141,12 +141,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile():
-    """dram bytes per launch of the lighting kernel from the committed ncu capture, if there is one."""
-    path = os.path.join(ROOT, "profiles", "light_kernel_traffic.json")
+def traffic_from_profile(kernel, config):
+    """measured DRAM bytes per launch of `kernel` on bench config `config` from the committed ncu captures (profiles/kernel_traffic.json),
+    or None when that combination has not been captured."""
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f)
+            return json.load(f).get("%s@%s" % (kernel, config))
     return None
 
 
@@ -460,9 +461,10 @@ def run_ours(args, scene, tiles, res, desc):
         b_compulsory = (28 * cl["voxelsLit"] + 112 * r_count / world) * scale
         achieved = b_light / (light_ms / 1000.0) / 1e9 if light_ms > 0 else 0.0
         b_draw = algorithmic_bytes_draw(cd)
-        traffic = traffic_from_profile()
-        roofline = {"kernel": "dn_light_flat_kernel" if e.stats()["lightLaunchesFlat"] > e.stats()["lightLaunchesWarp"] else "dn_light_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        light_name = "dn_light_flat_kernel" if e.stats()["lightLaunchesFlat"] > e.stats()["lightLaunchesWarp"] else "dn_light_kernel"
+        traffic = traffic_from_profile(light_name, args.config)
+        roofline = {"kernel": light_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": traffic,
                     "algorithmic_bytes_per_launch": b_light, "compulsory_bytes_per_launch": b_compulsory,
                     "compulsory_frac": (b_compulsory / (light_ms / 1000.0) / 1e9 / peak) if light_ms > 0 else 0.0,
                     "per_voxel": {k: cl[k] / max(cl["voxelsLit"], 1) for k in ("rays", "tiles", "chunks", "voxelSteps", "records")},
@@ -486,6 +488,7 @@ def run_ours(args, scene, tiles, res, desc):
                      "chunks_uploaded_per_step": (stats["chunksUploaded"] - stats0["chunksUploaded"]) / frames_run,
                      "bytes_uploaded_per_step": (stats["bytesUploaded"] - stats0["bytesUploaded"]) / frames_run,
                      "edits_per_s_end_to_end": EDITS_PER_FRAME / (frame2_ms / 1000.0) if frame2_ms > 0 else 0.0,
+                     "last_sync_host_ms": {"scan_sort": stats["lastScanHostMs"], "pack": stats["lastPackHostMs"], "alloc_enqueue": stats["lastEnqueueHostMs"]},
                      "note": "sync_compact includes the host-side packing of the dirty chunks and their upload on the side stream"}
         # draw, compaction count + scan + write, lighting, commit, visible merge; peer mode adds 2 barriers + the visible-bitmap merge,
         # collective mode one OR kernel per rank and bitmap

@@ -80,7 +80,8 @@ class DNb200stats(C.Structure):
                 ("slotCap", C.c_uint64), ("recordCap", C.c_uint64), ("voxelsLit", C.c_uint64),
                 ("lastDrawMs", C.c_float), ("lastCompactMs", C.c_float), ("lastUploadMs", C.c_float),
                 ("lastLightMs", C.c_float), ("lastCommitMs", C.c_float),
-                ("lightLaunchesWarp", C.c_uint64), ("lightLaunchesFlat", C.c_uint64), ("nsPerCtaWarp", C.c_float), ("nsPerCtaFlat", C.c_float)]
+                ("lightLaunchesWarp", C.c_uint64), ("lightLaunchesFlat", C.c_uint64), ("nsPerCtaWarp", C.c_float), ("nsPerCtaFlat", C.c_float),
+                ("lastScanHostMs", C.c_float), ("lastPackHostMs", C.c_float), ("lastEnqueueHostMs", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -67,8 +67,12 @@ DNB_FN f3 voxel_color(const DnbScene& S, uint32_t viewMode, uint4 rec, f3 colorA
 	return splat3(0.0f);
 }
 
+/* 4 CTAs per SM = 64 registers (32 warps per SM) with ~100 bytes of spills: 3-7 % faster than 80 registers / 3 CTAs on B200 */
+#ifndef DRAW_MIN_BLOCKS
+#define DRAW_MIN_BLOCKS 4
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(256) dn_draw_kernel(DnbScene S, DnbDrawParams P, float4* __restrict__ image, float4* __restrict__ mirror, DnbHit* __restrict__ hits)
+__global__ void __launch_bounds__(256, DRAW_MIN_BLOCKS) dn_draw_kernel(DnbScene S, DnbDrawParams P, float4* __restrict__ image, float4* __restrict__ mirror, DnbHit* __restrict__ hits)
 {
 	/* 32x8 pixel CTA made of 4x2 warp footprints of 8x4 pixels; blockIdx.y counts 8-row strips of the 16-pixel group rows
 	 * rowBegin, rowBegin + rowStride, ... this launch owns */

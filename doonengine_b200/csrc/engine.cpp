@@ -15,6 +15,7 @@
 #include <functional>
 #include <mutex>
 #include <math.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 #include <thread>
@@ -180,6 +181,14 @@ void fill_scene(VolumeImpl* v, DnbScene* s)
 }
 
 /* ---- timing helpers: device time of a kernel group, only when DN_b200_enable_timing(true) ---- */
+/* host wall-clock of the phases of a writing sync (always on: four clock reads per sync) */
+static inline double host_now_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
 struct ScopedTimer
 {
 	float* out;
@@ -550,7 +559,10 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 		}
 		arenaUsed[t] = cursor - begin * 512;
 	};
+	const double tPack0 = host_now_ms();
 	PackPool::get().run(workers, work);
+	const double tPack1 = host_now_ms();
+	v->stats.lastPackHostMs += (float)(tPack1 - tPack0);
 
 	/* serial: slots and record nodes */
 	size_t recordBytes = 0;
@@ -632,6 +644,7 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 	                                      v->slots.ptr, v->records.ptr, c.uploadStream), "scatter kernel");
 
 	v->stats.bytesUploaded += count * (sizeof(DnbUploadItem) + sizeof(DnbSlot)) + recordBytes;
+	v->stats.lastEnqueueHostMs += (float)(host_now_ms() - tPack1);
 	return ok;
 }
 
@@ -643,6 +656,8 @@ static void sync_write(VolumeImpl* v)
 		return;
 
 	ScopedTimer timer(&v->stats.lastUploadMs, c.uploadStream);
+	const double tScan0 = host_now_ms();
+	v->stats.lastPackHostMs = v->stats.lastEnqueueHostMs = 0.0f;
 
 	std::vector<PendingItem> pending;
 	pending.reserve(v->touched.size());
@@ -672,6 +687,7 @@ static void sync_write(VolumeImpl* v)
 
 	/* ascending tile order keeps slot / node assignment independent of edit order */
 	std::sort(pending.begin(), pending.end(), [](const PendingItem& a, const PendingItem& b) { return a.tile < b.tile; });
+	v->stats.lastScanHostMs = (float)(host_now_ms() - tScan0);
 
 	for(size_t at = 0; at < pending.size(); at += UPLOAD_BATCH)
 		if(!upload_batch(v, pending.data() + at, std::min(UPLOAD_BATCH, pending.size() - at)))

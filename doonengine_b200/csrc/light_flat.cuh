@@ -519,7 +519,11 @@ DNB_FN bool flat_setup_voxel(const DnbScene& S, const DnbStagingTargets& T, cons
 
 #define FLAT_WARPS 4
 
-__global__ void __launch_bounds__(FLAT_WARPS * 32) dn_light_flat_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
+/* 5 CTAs per SM = 96 registers with ~100 bytes of spills: 8 % faster than 119 registers / 4 CTAs on B200 (sparse map 90 -> 82.5 ms) */
+#ifndef FLAT_MIN_BLOCKS
+#define FLAT_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_flat_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
                                                                         uint32_t* __restrict__ workCounter, DnbStagingTargets T, DnbFlatTuning K)
 {
 	const uint32_t lane = threadIdx.x & 31u;

@@ -90,6 +90,7 @@ typedef struct DNb200stats
 	float    lastDrawMs, lastCompactMs, lastUploadMs, lastLightMs, lastCommitMs; /* device time of the last call of each kind, when timing is on */
 	uint64_t lightLaunchesWarp, lightLaunchesFlat;          /* lighting dispatches run by each kernel */
 	float    nsPerCtaWarp, nsPerCtaFlat;                    /* auto mode: running estimate of each kernel's time per 4 requests */
+	float    lastScanHostMs, lastPackHostMs, lastEnqueueHostMs; /* host wall-clock of the last writing sync: dirty-tile scan + sort, packing, allocation + enqueue */
 } DNb200stats;
 void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
 void DN_b200_enable_timing(bool enable); /* record CUDA events around each kernel group (adds a sync when read) */

@@ -27,16 +27,20 @@ fb = e.framebuffer(w, h)
 view, proj = e.view_projection(h / w)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-variants = [("warp", None)] + [("flat", k) for k in [(24, 28, 16), (24, 32, 16), (24, 16, 16)]]
+variants = [("warp", None), ("flat", (24, 28, 16))]
 out = []
 k = 0
 for name, knobs in variants:
     L.DN_b200_set_light_kernel(1 if name == "flat" else 0)
     if knobs:
         L.DN_b200_set_flat_tuning(*knobs)
-    times = []
+    times, dtimes = [], []
     for f in range(frames + 2):
+        flush.fill_(f & 255)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
         L.DN_draw(e.vol, fb, view, proj, -1, -1)
+        d1.record(stream)
         L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
         flush.fill_(f & 255)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -48,6 +52,7 @@ for name, knobs in variants:
         k += 1
         if f >= 2:
             times.append(a.elapsed_time(b))
-    rec = {"config": cfg, "kernel": name, "knobs": knobs, "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "requests": int(e.vol.contents.numLightingRequests)}
+            dtimes.append(d0.elapsed_time(d1))
+    rec = {"config": cfg, "kernel": name, "knobs": knobs, "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "draw_ms_median": float(np.median(dtimes)), "requests": int(e.vol.contents.numLightingRequests)}
     print(json.dumps(rec), flush=True)
     out.append(rec)

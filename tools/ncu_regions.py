@@ -46,4 +46,6 @@ ti = sum(d[0] for d in agg.values()) or 1
 ts = sum(d[2] for d in agg.values()) or 1
 print("warp instructions %.4e, avg lanes %.2f" % (ti, sum(d[1] for d in agg.values()) / ti))
 for k, d in sorted(agg.items(), key=lambda x: -x[1][0]):
+    if d[0] / ti < 0.001:
+        continue
     print("%-60s inst %5.1f%%  samples %5.1f%%  lanes %.1f" % (k, 100 * d[0] / ti, 100 * d[2] / ts, d[1] / max(d[0], 1)))
