@@ -184,6 +184,8 @@ _PROTOTYPES = {
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
     "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
+    "DN_b200_save_lighting": (C.c_bool, [C.POINTER(DNvolume), C.c_char_p]),
+    "DN_b200_load_lighting": (C.c_int, [C.POINTER(DNvolume), C.c_char_p]),
     "DN_b200_set_shard": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int]),
     "DN_b200_light_compute": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int, C.c_float]),
     "DN_b200_light_commit": (C.c_bool, [C.POINTER(DNvolume)]),

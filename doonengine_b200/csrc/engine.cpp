@@ -1754,3 +1754,125 @@ extern "C" bool DN_b200_peer_barrier_status(DNvolume* vol, uint64_t* epochs, uin
 	}
 	return true;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* lit-state checkpoint: the reference saves only the map (voxel.c:595-654); after a load every chunk */
+/* re-accumulates its lighting from zero samples.  These two calls carry the accumulated lighting across a save / load.  */
+
+namespace
+{
+struct LitFileHeader
+{
+	char     magic[8];   /* "DNLIT001" */
+	uint32_t mapSize[3];
+	uint32_t numChunks;
+};
+struct LitChunkHeader
+{
+	uint32_t mapIndex, numVoxels, numSamples, pad;
+	uint32_t mask[16];   /* the surface mask the words belong to: a chunk edited since the checkpoint is skipped on load */
+};
+} // namespace
+
+extern "C" bool DN_b200_save_lighting(DNvolume* vol, const char* filePath)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_b200_save_lighting") || !DN_b200_synchronize())
+		return false;
+	std::vector<DnbSlot> slots(v->slotTop);
+	std::vector<uint4> records(v->recordTop);
+	if((v->slotTop && !cuda_ok(cudaMemcpy(slots.data(), v->slots.ptr, slots.size() * sizeof(DnbSlot), cudaMemcpyDeviceToHost), "slot download")) ||
+	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")))
+		return false;
+	FILE* f = fopen(filePath, "wb");
+	if(!f)
+	{
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "failed to open file \"%s\" for writing", filePath);
+		return false;
+	}
+	LitFileHeader h;
+	memcpy(h.magic, "DNLIT001", 8);
+	h.mapSize[0] = vol->mapSize.x; h.mapSize[1] = vol->mapSize.y; h.mapSize[2] = vol->mapSize.z;
+	h.numChunks = 0;
+	const size_t tiles = num_tiles(vol);
+	for(size_t t = 0; t < tiles; t++)
+		h.numChunks += v->tileSlotHost[t] != 0;
+	bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+	for(size_t t = 0; t < tiles && ok; t++)
+	{
+		if(!v->tileSlotHost[t])
+			continue;
+		const DnbSlot& s = slots[v->tileSlotHost[t] - 1];
+		LitChunkHeader c;
+		c.mapIndex = (uint32_t)t; c.numVoxels = s.numVoxels; c.numSamples = s.numSamples; c.pad = 0;
+		memcpy(c.mask, s.mask, sizeof(c.mask));
+		ok = fwrite(&c, sizeof(c), 1, f) == 1 && (s.numVoxels == 0 || fwrite(&records[s.voxelBase], sizeof(uint4), s.numVoxels, f) == s.numVoxels);
+	}
+	fclose(f);
+	if(!ok)
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "failed to write lighting checkpoint \"%s\"", filePath);
+	return ok;
+}
+
+/* returns the number of chunks whose lighting was restored, -1 on error.  Call after the map is resident (a writing sync). */
+extern "C" int DN_b200_load_lighting(DNvolume* vol, const char* filePath)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!device_ready(v, "DN_b200_load_lighting") || !DN_b200_synchronize())
+		return -1;
+	FILE* f = fopen(filePath, "rb");
+	if(!f)
+	{
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "failed to open file \"%s\" for reading", filePath);
+		return -1;
+	}
+	LitFileHeader h;
+	if(fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "DNLIT001", 8) != 0 || h.mapSize[0] != vol->mapSize.x || h.mapSize[1] != vol->mapSize.y || h.mapSize[2] != vol->mapSize.z)
+	{
+		fclose(f);
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "\"%s\" is not a lighting checkpoint of a %ux%ux%u map", filePath, vol->mapSize.x, vol->mapSize.y, vol->mapSize.z);
+		return -1;
+	}
+	std::vector<DnbSlot> slots(v->slotTop);
+	std::vector<uint4> records(v->recordTop);
+	if((v->slotTop && !cuda_ok(cudaMemcpy(slots.data(), v->slots.ptr, slots.size() * sizeof(DnbSlot), cudaMemcpyDeviceToHost), "slot download")) ||
+	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")))
+	{
+		fclose(f);
+		return -1;
+	}
+	int restored = 0;
+	bool ok = true;
+	std::vector<uint4> saved(512);
+	const size_t tiles = num_tiles(vol);
+	for(uint32_t k = 0; k < h.numChunks && ok; k++)
+	{
+		LitChunkHeader c;
+		ok = fread(&c, sizeof(c), 1, f) == 1 && c.numVoxels <= 512;
+		if(!ok)
+			break;
+		ok = c.numVoxels == 0 || fread(saved.data(), sizeof(uint4), c.numVoxels, f) == c.numVoxels;
+		if(!ok || c.mapIndex >= tiles || !v->tileSlotHost[c.mapIndex])
+			continue;
+		DnbSlot& s = slots[v->tileSlotHost[c.mapIndex] - 1];
+		/* edited since the checkpoint (surface, material, normal or albedo of any voxel): its lighting restarts, as after any edit (voxel.c:1401) */
+		bool same = s.numVoxels == c.numVoxels && memcmp(s.mask, c.mask, sizeof(c.mask)) == 0;
+		for(uint32_t i = 0; i < c.numVoxels && same; i++)
+			same = records[s.voxelBase + i].x == saved[i].x && (records[s.voxelBase + i].y >> 8) == (saved[i].y >> 8);
+		if(!same)
+			continue;
+		memcpy(&records[s.voxelBase], saved.data(), (size_t)c.numVoxels * sizeof(uint4));
+		s.numSamples = c.numSamples;
+		restored++;
+	}
+	fclose(f);
+	if(!ok)
+	{
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "lighting checkpoint \"%s\" is truncated", filePath);
+		return -1;
+	}
+	if((v->slotTop && !cuda_ok(cudaMemcpy(v->slots.ptr, slots.data(), slots.size() * sizeof(DnbSlot), cudaMemcpyHostToDevice), "slot upload")) ||
+	   (v->recordTop && !cuda_ok(cudaMemcpy(v->records.ptr, records.data(), records.size() * sizeof(uint4), cudaMemcpyHostToDevice), "record upload")))
+		return -1;
+	return restored;
+}

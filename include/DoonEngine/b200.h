@@ -107,6 +107,14 @@ int DN_b200_pack_chunk(DNvolume* vol, DNivec3 mapPos, void* slotOut128, void* re
  * material DN_MATERIAL_EMPTY removes; positions outside the map are skipped; returns the number of edits applied */
 size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions, const DNcompressedVoxel* voxels); /* marks every tile touched: the next writing sync reconciles the whole map */
 
+/* ---- lit-state checkpoint: DN_save_volume / DN_load_volume persist only the map (voxel.c:520-654), so upstream every chunk
+ * re-accumulates its lighting from zero samples after a load.  These carry the accumulated lighting (the three lit words of every
+ * record + each chunk's sample count) across: save any time; load after DN_load_volume + a writing DN_sync_gpu.  Chunks whose
+ * surface mask changed since the checkpoint are skipped (their lighting restarts, as after any edit).  load returns the number of
+ * chunks restored, -1 on error. ---- */
+bool DN_b200_save_lighting(DNvolume* vol, const char* filePath);
+int  DN_b200_load_lighting(DNvolume* vol, const char* filePath);
+
 /* ---- multi-GPU: one process per GPU, the same volume replicated in each ---- */
 /* this process lights requests [rank*ceil(R/world), ...) and draws the rank-th band of 16-pixel rows */
 bool DN_b200_set_shard(DNvolume* vol, int rank, int worldSize);
