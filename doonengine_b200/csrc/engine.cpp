@@ -1231,7 +1231,9 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 		{
 			const int k = t.slotKernel[slot];
 			const double ns = 1e6 * (double)ms / (double)t.slotCtas[slot];
-			t.nsPerCta[k] = t.samples[k] == 0 ? ns : 0.5 * t.nsPerCta[k] + 0.5 * ns;
+			/* running minimum that may rise by at most 3 % per sample: interference (another process on the box, a clock dip)
+			 * only ever makes a dispatch slower, so one slow sample must not dethrone the faster kernel */
+			t.nsPerCta[k] = t.samples[k] == 0 ? ns : std::min(ns, 1.03 * t.nsPerCta[k]);
 			t.samples[k]++;
 		}
 		t.slotKernel[slot] = -1;
@@ -1244,9 +1246,13 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 		k = (int)(n & 1u) ^ 1;                     /* flat, warp, flat, warp ... until both have two timings */
 	else
 	{
-		k = t.nsPerCta[1] <= t.nsPerCta[0] ? 1 : 0;
+		/* hysteresis: the kernel that ran last keeps running unless the other one is at least 5 % faster */
+		const int last = t.lastKernel;
+		k = t.nsPerCta[last ^ 1] < 0.95 * t.nsPerCta[last] ? (last ^ 1) : last;
 		if((n & 63u) == 63u)
-			k ^= 1;                                  /* keep the loser's estimate fresh */
+			k ^= 1;                                  /* keep the other kernel's estimate fresh */
+		else
+			t.lastKernel = k;
 	}
 
 	/* time this dispatch if a slot is free (never the first dispatch of a volume) */
@@ -1769,7 +1775,8 @@ struct LitFileHeader
 };
 struct LitChunkHeader
 {
-	uint32_t mapIndex, numVoxels, numSamples, pad;
+	uint32_t mapIndex, numVoxels, numSamples;
+	uint32_t visible;    /* the chunk's visible bit: specular hits of the last pass may have raised it (LI:101-105), so it is lighting state */
 	uint32_t mask[16];   /* the surface mask the words belong to: a chunk edited since the checkpoint is skipped on load */
 };
 } // namespace
@@ -1781,8 +1788,10 @@ extern "C" bool DN_b200_save_lighting(DNvolume* vol, const char* filePath)
 		return false;
 	std::vector<DnbSlot> slots(v->slotTop);
 	std::vector<uint4> records(v->recordTop);
+	std::vector<uint32_t> visible((num_tiles(vol) + 31) / 32);
 	if((v->slotTop && !cuda_ok(cudaMemcpy(slots.data(), v->slots.ptr, slots.size() * sizeof(DnbSlot), cudaMemcpyDeviceToHost), "slot download")) ||
-	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")))
+	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")) ||
+	   (!visible.empty() && !cuda_ok(cudaMemcpy(visible.data(), v->visible.ptr, visible.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost), "visible bitmap download")))
 		return false;
 	FILE* f = fopen(filePath, "wb");
 	if(!f)
@@ -1804,7 +1813,8 @@ extern "C" bool DN_b200_save_lighting(DNvolume* vol, const char* filePath)
 			continue;
 		const DnbSlot& s = slots[v->tileSlotHost[t] - 1];
 		LitChunkHeader c;
-		c.mapIndex = (uint32_t)t; c.numVoxels = s.numVoxels; c.numSamples = s.numSamples; c.pad = 0;
+		c.mapIndex = (uint32_t)t; c.numVoxels = s.numVoxels; c.numSamples = s.numSamples;
+		c.visible = (visible[t >> 5] >> (t & 31)) & 1u;
 		memcpy(c.mask, s.mask, sizeof(c.mask));
 		ok = fwrite(&c, sizeof(c), 1, f) == 1 && (s.numVoxels == 0 || fwrite(&records[s.voxelBase], sizeof(uint4), s.numVoxels, f) == s.numVoxels);
 	}
@@ -1835,8 +1845,10 @@ extern "C" int DN_b200_load_lighting(DNvolume* vol, const char* filePath)
 	}
 	std::vector<DnbSlot> slots(v->slotTop);
 	std::vector<uint4> records(v->recordTop);
+	std::vector<uint32_t> visible((num_tiles(vol) + 31) / 32);
 	if((v->slotTop && !cuda_ok(cudaMemcpy(slots.data(), v->slots.ptr, slots.size() * sizeof(DnbSlot), cudaMemcpyDeviceToHost), "slot download")) ||
-	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")))
+	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")) ||
+	   (!visible.empty() && !cuda_ok(cudaMemcpy(visible.data(), v->visible.ptr, visible.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost), "visible bitmap download")))
 	{
 		fclose(f);
 		return -1;
@@ -1863,6 +1875,8 @@ extern "C" int DN_b200_load_lighting(DNvolume* vol, const char* filePath)
 			continue;
 		memcpy(&records[s.voxelBase], saved.data(), (size_t)c.numVoxels * sizeof(uint4));
 		s.numSamples = c.numSamples;
+		if(c.visible)
+			visible[c.mapIndex >> 5] |= 1u << (c.mapIndex & 31u);
 		restored++;
 	}
 	fclose(f);
@@ -1871,6 +1885,8 @@ extern "C" int DN_b200_load_lighting(DNvolume* vol, const char* filePath)
 		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "lighting checkpoint \"%s\" is truncated", filePath);
 		return -1;
 	}
+	if(!visible.empty() && !cuda_ok(cudaMemcpy(v->visible.ptr, visible.data(), visible.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "visible bitmap upload"))
+		return -1;
 	if((v->slotTop && !cuda_ok(cudaMemcpy(v->slots.ptr, slots.data(), slots.size() * sizeof(DnbSlot), cudaMemcpyHostToDevice), "slot upload")) ||
 	   (v->recordTop && !cuda_ok(cudaMemcpy(v->records.ptr, records.data(), records.size() * sizeof(uint4), cudaMemcpyHostToDevice), "record upload")))
 		return -1;

@@ -109,6 +109,7 @@ struct VolumeImpl
 		uint32_t samples[2] = {0, 0};
 		uint64_t dispatches = 0;
 		uint64_t launches[2] = {0, 0};
+		int      lastKernel = 1;
 	} tuner;
 
 	/* ---- multi-GPU over peer memory (DoonEngine/b200.h) ---- */

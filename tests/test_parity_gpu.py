@@ -451,6 +451,8 @@ def test_lighting_checkpoint_round_trip(dn, tmp_path):
     vox, lit = str(tmp_path / "map.voxvol").encode(), str(tmp_path / "map.lit").encode()
     assert a.L.DN_save_volume(vox, a.vol)
     assert a.L.DN_b200_save_lighting(a.vol, lit)
+    snap = records_by_tile(a)
+    assert snap["samples"].any()
 
     b = dn.Engine(voxvol=vox.decode(), min_chunks=256)
     b.sync(1, 1)
@@ -458,9 +460,9 @@ def test_lighting_checkpoint_round_trip(dn, tmp_path):
     assert not fresh["samples"].any()
     assert b.L.DN_b200_load_lighting(b.vol, lit) == len(fresh["tiles"])
     sa, sb = records_by_tile(a), records_by_tile(b)
-    for key in ("tiles", "counts", "masks", "records", "samples"):
+    for key in ("tiles", "counts", "masks", "records", "samples", "visible"):
         assert np.array_equal(sa[key], sb[key]), key
-    # both continue identically (the visible bits are not part of the checkpoint: the next draw sets them)
+    # both continue identically
     for k in range(3, 5):
         ia = a.frame(W, H, frame_time(k))
         ib = b.frame(W, H, frame_time(k))
@@ -480,6 +482,6 @@ def test_lighting_checkpoint_round_trip(dn, tmp_path):
     c.sync(1, 1)
     assert c.L.DN_b200_load_lighting(c.vol, lit) == len(fresh["tiles"]) - 1
     sc = records_by_tile(c)
-    assert int(sc["samples"][0]) == 0 and sc["samples"][1:].all()
+    assert int(sc["samples"][0]) == 0 and np.array_equal(sc["samples"][1:], snap["samples"][1:])
     for e in (a, b, c):
         e.close()
