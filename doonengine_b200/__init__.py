@@ -184,6 +184,7 @@ _PROTOTYPES = {
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
     "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
+    "DN_b200_set_chunks": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
     "DN_b200_save_lighting": (C.c_bool, [C.POINTER(DNvolume), C.c_char_p]),
     "DN_b200_load_lighting": (C.c_int, [C.POINTER(DNvolume), C.c_char_p]),
     "DN_b200_set_shard": (C.c_bool, [C.POINTER(DNvolume), C.c_int, C.c_int]),
@@ -368,6 +369,13 @@ class Engine:
         ch["numVoxels"][ci] = n
         ch["updated"][ci] = 1
         self.L.DN_b200_touch_tile(self.vol, mp)
+
+    def set_chunks(self, positions, voxels):
+        """bulk form of set_chunk: positions int32 [n,3] (tiles), voxels uint32 [n,8,8,8,2]; returns the chunks present afterwards."""
+        p = np.ascontiguousarray(positions, dtype=np.int32)
+        v = np.ascontiguousarray(voxels, dtype=np.uint32)
+        assert p.ndim == 2 and p.shape[1] == 3 and v.shape == (p.shape[0], 8, 8, 8, 2)
+        return int(self.L.DN_b200_set_chunks(self.vol, p.shape[0], p.ctypes.data, v.ctypes.data))
 
     def set_voxels(self, positions, voxels):
         """bulk edits: positions int32 [n,3] in voxel units, voxels uint32 [n,2] (normal word, albedo word); material 255 removes."""

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdoon_b200.so")
+SCENES_LIB = os.path.join(HERE, "libdoon_scenes.so")  # native generators of the large synthetic maps (bench / tests only)
 
 SOURCES = ["draw.cu", "light.cu", "compact.cu", "upload.cu", "peer.cu", "engine.cpp", "volume_host.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh")))  # every header: a stale library is worse than a slow build
@@ -46,12 +47,22 @@ def up_to_date():
     return all(os.path.getmtime(f) <= t for f in _inputs())
 
 
+def build_scenes(force=False):
+    """gcc -> libdoon_scenes.so: csrc/scenegen.c, the native twin of scenes.sparse_balls / dense_corridors."""
+    src = os.path.join(CSRC, "scenegen.c")
+    if not force and os.path.exists(SCENES_LIB) and os.path.getmtime(SCENES_LIB) >= os.path.getmtime(src):
+        return SCENES_LIB
+    subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-Wall", "-o", SCENES_LIB, src])
+    return SCENES_LIB
+
+
 def build(force=False, verbose=False, defines=(), out=None):
     """compile (if stale) and return the path of the shared library.  `defines` / `out` build an experimental variant
     (e.g. defines=["FLAT_FIRST_STEP=1"], out="libdoon_b200_v1.so"; load it with $DN_B200_LIB)."""
     global LIB
     if out:
         return _build_variant(defines, out, verbose)
+    build_scenes(force)
     if not force and up_to_date():
         return LIB
     objdir = os.path.join(HERE, "build")

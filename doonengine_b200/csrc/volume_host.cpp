@@ -795,6 +795,46 @@ extern "C" size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3*
 	return applied;
 }
 
+/* `count` whole chunks in one call: the bulk form of 512 DN_set_compressed_voxel calls per chunk (voxel.c:1126-1160), as the map
+ * loader does it (voxel.c:560-640).  voxels = count x [8][8][8] DNcompressedVoxel in the chunk's own [x][y][z] order; a chunk without a
+ * single solid voxel removes the tile's chunk.  Tiles outside the map are skipped.  Returns the number of chunks now present. */
+extern "C" size_t DN_b200_set_chunks(DNvolume* vol, size_t count, const DNivec3* mapPositions, const DNcompressedVoxel* voxels)
+{
+	size_t present = 0;
+	for(size_t i = 0; i < count; i++)
+	{
+		const DNivec3 mp = mapPositions[i];
+		if(!DN_in_map_bounds(vol, mp))
+			continue;
+		const DNcompressedVoxel* src = voxels + i * 512;
+		uint32_t solid = 0;
+		for(int k = 0; k < 512; k++)
+			solid += (src[k].normal >> 24) != DN_MATERIAL_EMPTY;
+		const size_t mapIndex = DN_FLATTEN_INDEX(mp, vol->mapSize);
+		if(solid == 0)
+		{
+			if(vol->map[mapIndex].flag != 0)
+				DN_remove_chunk(vol, mp);
+			continue;
+		}
+		if(vol->map[mapIndex].flag == 0 && DN_add_chunk(vol, mp) < 0)
+			break;
+		DNchunk* chunk = &vol->chunks[vol->map[mapIndex].chunkIndex];
+		DNcompressedVoxel* dst = &chunk->voxels[0][0][0];
+		for(int k = 0; k < 512; k++)
+		{
+			dst[k] = src[k];
+			if((src[k].normal >> 24) == DN_MATERIAL_EMPTY)
+				dst[k].normal = UINT32_MAX; /* what DN_remove_voxel leaves behind (voxel.c:1178) */
+		}
+		chunk->numVoxels = solid;
+		chunk->updated = true;
+		touch_tile(impl_of(vol), mapIndex);
+		present++;
+	}
+	return present;
+}
+
 extern "C" void DN_b200_touch_tile(DNvolume* vol, DNivec3 mapPos)
 {
 	if(DN_in_map_bounds(vol, mapPos))

@@ -286,6 +286,83 @@ def mixed_camera(tiles=(6, 4, 6)):
     return dict(camPos=(-0.6, 2.6, -0.8), camOrient=(22.0, 42.0, 0.0), camFOV=90.0)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# native twins of sparse_balls / dense_corridors (csrc/scenegen.c -> libdoon_scenes.so): whole z-slabs of chunks at a time,
+# bit-identical to the numpy generators above (tests/test_abi_host.py), fast enough for the full-size configs 3 and 5
+_native = None
+
+
+def native_lib():
+    global _native
+    if _native is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdoon_scenes.so")
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing: run `python -m doonengine_b200.build`" % path)
+        L = C.CDLL(path)
+        L.dnscene_sparse_balls.restype = C.c_size_t
+        L.dnscene_sparse_balls.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.dnscene_dense_corridors.restype = C.c_size_t
+        L.dnscene_dense_corridors.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        _native = L
+    return _native
+
+
+def _normal24_table():
+    X, Y, Z, _ = _ball_offsets()
+    b = compress_normal(max_normalise(np.stack([X, Y, Z], axis=-1)))
+    return np.ascontiguousarray(((b[..., 0] << np.uint32(16)) | (b[..., 1] << np.uint32(8)) | b[..., 2]).astype(np.uint32).reshape(512))
+
+
+def native_slabs(scene, tiles, slab=1, fill=0.2, seed=None, period=4, material=5):
+    """yields (positions int32 [n,3], voxels uint32 [n,8,8,8,2]) for `slab` z-layers of tiles at a time, in the order of the numpy
+    generators (z, then y, then x).  scene: "sparse" | "dense"."""
+    L = native_lib()
+    t = np.array(tiles, np.uint32)
+    n24 = _normal24_table()
+    dist = np.ascontiguousarray(_ball_offsets()[3].astype(np.float32).reshape(512))
+    for z0 in range(0, tiles[2], slab):
+        z1 = min(tiles[2], z0 + slab)
+        if scene == "sparse":
+            threshold = min(0xFFFFFFFF, int(fill * 4294967296.0))
+            sd = 99 if seed is None else seed
+            call = lambda p, v, cap: L.dnscene_sparse_balls(t.ctypes.data, threshold, sd, z0, z1, dist.ctypes.data, n24.ctypes.data, p, v, cap)
+        elif scene == "dense":
+            sd = 5 if seed is None else seed
+            call = lambda p, v, cap: L.dnscene_dense_corridors(t.ctypes.data, period, material, sd, z0, z1, n24.ctypes.data, p, v, cap)
+        else:
+            raise ValueError(scene)
+        n = int(call(None, None, 0))
+        if n == 0:
+            continue
+        pos = np.empty((n, 3), np.int32)
+        vox = np.empty((n, 8, 8, 8, 2), np.uint32)
+        call(pos.ctypes.data, vox.ctypes.data, n)
+        yield pos, vox
+
+
+def native_count(scene, tiles, **kw):
+    """number of chunks the native generator will produce (cheap: hashes only for "sparse", arithmetic for "dense")."""
+    L = native_lib()
+    t = np.array(tiles, np.uint32)
+    if scene == "sparse":
+        threshold = min(0xFFFFFFFF, int(kw.get("fill", 0.2) * 4294967296.0))
+        return int(L.dnscene_sparse_balls(t.ctypes.data, threshold, kw.get("seed", 99), 0, tiles[2], None, None, None, None, 0))
+    return int(L.dnscene_dense_corridors(t.ctypes.data, kw.get("period", 4), kw.get("material", 5), kw.get("seed", 5), 0, tiles[2], None, None, None, 0))
+
+
+def build_native(engine, scene, tiles, materials=None, slab=2, **params):
+    """the large maps through the bulk path: native generator -> engine.set_chunks, a few z-layers at a time."""
+    engine.materials()[:] = default_materials() if materials is None else materials
+    n = 0
+    for pos, vox in native_slabs(scene, tiles, slab=slab):
+        n += engine.set_chunks(pos, vox)
+    if params:
+        engine.set_params(**params)
+    return n
+
+
 def build(engine, chunks, materials=None, **params):
     """feed a chunk stream and a material table to any engine (CUDA, oracle or reference); returns the chunk count."""
     if materials is None:

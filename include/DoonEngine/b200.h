@@ -107,6 +107,11 @@ int DN_b200_pack_chunk(DNvolume* vol, DNivec3 mapPos, void* slotOut128, void* re
  * material DN_MATERIAL_EMPTY removes; positions outside the map are skipped; returns the number of edits applied */
 size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions, const DNcompressedVoxel* voxels); /* marks every tile touched: the next writing sync reconciles the whole map */
 
+/* `count` whole chunks in one call (the loader's bulk path, voxel.c:560-640, for procedurally built maps): voxels = count x [8][8][8]
+ * DNcompressedVoxel in the chunk's own [x][y][z] order; a chunk without a solid voxel removes the tile's chunk; tiles outside the map
+ * are skipped; returns the number of chunks present afterwards among those given */
+size_t DN_b200_set_chunks(DNvolume* vol, size_t count, const DNivec3* mapPositions, const DNcompressedVoxel* voxels);
+
 /* ---- lit-state checkpoint: DN_save_volume / DN_load_volume persist only the map (voxel.c:520-654), so upstream every chunk
  * re-accumulates its lighting from zero samples after a load.  These carry the accumulated lighting (the three lit words of every
  * record + each chunk's sample count) across: save any time; load after DN_load_volume + a writing DN_sync_gpu.  Chunks whose

@@ -226,3 +226,49 @@ def test_host_packing_matches_oracle(oracle_mod):
                     e.set_chunk((x, y, z), vox)
     compare(p, o, "random")
     p.close(); o.close()
+
+
+def test_native_scene_generators_match_numpy(dn):
+    """csrc/scenegen.c (the generator of the full-size configs 3 and 5) yields the same chunks, in the same order, as scenes.py."""
+    from doonengine_b200 import scenes
+    for scene, tiles, ref in (("sparse", (12, 9, 7), scenes.sparse_balls), ("dense", (7, 6, 9), scenes.dense_corridors)):
+        want = list(ref(tiles))
+        assert scenes.native_count(scene, tiles) == len(want) > 0
+        for slab in (1, 4):
+            pos = np.concatenate([p for p, _ in scenes.native_slabs(scene, tiles, slab=slab)])
+            vox = np.concatenate([v for _, v in scenes.native_slabs(scene, tiles, slab=slab)])
+            assert pos.shape[0] == len(want)
+            assert np.array_equal(pos, np.array([p for p, _ in want], np.int32))
+            assert np.array_equal(vox, np.stack([v for _, v in want]))
+
+
+def test_bulk_chunks_equal_single_chunks(dn):
+    """DN_b200_set_chunks leaves the host map exactly as per-chunk writes do, incl. empty chunks removing a tile's chunk."""
+    from doonengine_b200 import scenes
+    tiles = (6, 5, 4)
+    want = list(scenes.sparse_balls(tiles))
+    a = dn.Engine(map_size=tiles, min_chunks=4, host_only=True)
+    b = dn.Engine(map_size=tiles, min_chunks=4, host_only=True)
+    for p, v in want:
+        a.set_chunk(p, v)
+    assert b.set_chunks(np.array([p for p, _ in want], np.int32), np.stack([v for _, v in want])) == len(want)
+    # clear one chunk through both paths; an out-of-map tile is skipped
+    p0, v0 = want[3]
+    empty = np.full_like(v0, 0xFFFFFFFF)
+    a.set_chunk(p0, empty)
+    assert b.set_chunks(np.array([p0, (99, 0, 0)], np.int32), np.stack([empty, v0])) == 0
+    ma, mb = a.host_map(), b.host_map()
+    assert np.array_equal(ma["flag"], mb["flag"])
+    ca, cb = a.host_chunks(), b.host_chunks()
+    for t in np.nonzero(ma["flag"])[0]:
+        x, y = ca[ma["chunkIndex"][t]], cb[mb["chunkIndex"][t]]
+        assert x["numVoxels"] == y["numVoxels"] and np.array_equal(x["voxels"], y["voxels"]) and y["updated"]
+    assert int(ma["flag"].astype(bool).sum()) == len(want) - 1
+    # and both pack to the same upload bytes
+    for p, _ in want[:8]:
+        pa, pb = a.pack_chunk(p), b.pack_chunk(p)
+        assert (pa is None) == (pb is None)
+        if pa is not None:
+            assert pa[0].tobytes() == pb[0].tobytes() and np.array_equal(pa[1], pb[1])
+    a.close()
+    b.close()
