@@ -267,7 +267,7 @@ def run_ours(args, scene, tiles, res, desc):
     w, h = res
     L = dn.lib()
     dn.init(device=local)
-    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "auto": 2}[args.light_kernel])
+    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "auto": 2, "wave": 3}[args.light_kernel])
     # a non-default stream shared by torch (events, collectives, copies) and the library's kernels
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
@@ -472,7 +472,8 @@ def run_ours(args, scene, tiles, res, desc):
         b_compulsory = (28 * cl["voxelsLit"] + 112 * r_count / world) * scale
         achieved = b_light / (light_ms / 1000.0) / 1e9 if light_ms > 0 else 0.0
         b_draw = algorithmic_bytes_draw(cd)
-        light_name = "dn_light_flat_kernel" if e.stats()["lightLaunchesFlat"] > e.stats()["lightLaunchesWarp"] else "dn_light_kernel"
+        st_ = e.stats()
+        light_name = max((("dn_light_kernel", st_["lightLaunchesWarp"]), ("dn_light_flat_kernel", st_["lightLaunchesFlat"]), ("dn_wave_step_kernel", st_["lightLaunchesWave"])), key=lambda kv: kv[1])[0]
         traffic = traffic_from_profile(light_name, args.config)
         roofline = {"kernel": light_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "traffic": traffic,
@@ -512,8 +513,9 @@ def run_ours(args, scene, tiles, res, desc):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "parallelism": ("map replicated, request CTAs and 16-pixel rows interleaved x%d, exchange=%s" % (world, sh.exchange)) if world > 1 else "1 GPU",
-                       "light_kernel": {"mode": args.light_kernel, "dispatches_warp_per_request": int(stats["lightLaunchesWarp"]), "dispatches_persistent": int(stats["lightLaunchesFlat"]),
-                                        "ns_per_4_requests": {"warp": stats["nsPerCtaWarp"], "persistent": stats["nsPerCtaFlat"]}}, "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
+                       "light_kernel": {"mode": args.light_kernel, "dispatches_warp_per_request": int(stats["lightLaunchesWarp"]), "dispatches_persistent": int(stats["lightLaunchesFlat"]), "dispatches_wavefront": int(stats["lightLaunchesWave"]),
+                                        "wavefront_passes_last": int(stats["lastWavePasses"]),
+                                        "ns_per_4_requests": {"warp": stats["nsPerCtaWarp"], "persistent": stats["nsPerCtaFlat"], "wavefront": stats["nsPerCtaWave"]}}, "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
                        "resident_records": int(stats["residentRecords"]), "requests_per_step": reqs / K, "voxels_lit_per_step": lit / K, "build_s": t_build},
             "frame_ms": {"draw": draw_ms, "sync_compact": sync_ms, "light_kernel": light_ms, "commit": commit_ms, "frame": frame_ms, "frame_with_readback": frame2_ms,
                          "wall_per_step_incl_flush": 1000.0 * wall / K},
@@ -552,7 +554,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--light-kernel", default="auto", choices=["auto", "flat", "warp"], help="auto (default): the library times both lighting kernels on live dispatches and runs the faster one")
+    ap.add_argument("--light-kernel", default="auto", choices=["auto", "flat", "warp", "wave"], help="auto (default): the library times its three lighting kernels on live dispatches and runs the fastest one")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"], help="N > 1: kernels exchange over peer memory (default) or host-driven NCCL all-gathers")
     ap.add_argument("--sampler-ms", type=float, default=10.0, help="NVML clock sampling period during the timed region (0 = off)")
     args = ap.parse_args()

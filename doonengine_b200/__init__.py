@@ -81,7 +81,8 @@ class DNb200stats(C.Structure):
                 ("lastDrawMs", C.c_float), ("lastCompactMs", C.c_float), ("lastUploadMs", C.c_float),
                 ("lastLightMs", C.c_float), ("lastCommitMs", C.c_float),
                 ("lightLaunchesWarp", C.c_uint64), ("lightLaunchesFlat", C.c_uint64), ("nsPerCtaWarp", C.c_float), ("nsPerCtaFlat", C.c_float),
-                ("lastScanHostMs", C.c_float), ("lastPackHostMs", C.c_float), ("lastEnqueueHostMs", C.c_float)]
+                ("lastScanHostMs", C.c_float), ("lastPackHostMs", C.c_float), ("lastEnqueueHostMs", C.c_float),
+                ("lightLaunchesWave", C.c_uint64), ("nsPerCtaWave", C.c_float), ("lastWavePasses", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -184,6 +185,7 @@ _PROTOTYPES = {
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
     "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
+    "DN_b200_set_wave_slots": (None, [C.c_uint32]),
     "DN_b200_set_chunks": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
     "DN_b200_save_lighting": (C.c_bool, [C.POINTER(DNvolume), C.c_char_p]),
     "DN_b200_load_lighting": (C.c_int, [C.POINTER(DNvolume), C.c_char_p]),
@@ -465,7 +467,7 @@ class Engine:
         n = self.L.DN_b200_array_bytes(self.vol, which)
         out = np.zeros(n // np.dtype(dtype).itemsize, dtype=dtype)
         if n and self.L.DN_b200_download(self.vol, which, out.ctypes.data, out.nbytes) != n:
-            raise RuntimeError("DN_b200_download failed")
+            raise RuntimeError("DN_b200_download failed: %s" % (messages()[-1][2] if messages() else "?"))
         return out
 
     def requests(self):

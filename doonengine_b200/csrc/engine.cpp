@@ -134,7 +134,7 @@ void device_destroy(VolumeImpl* v)
 	}
 	device_free(v->tileSlot); device_free(v->occ64); device_free(v->visible); device_free(v->propagate); device_free(v->forced);
 	device_free(v->slots); device_free(v->records); device_free(v->materials); device_free(v->requests); device_free(v->staging);
-	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->blob); device_free(v->litCounter);
+	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->waveCtx); device_free(v->blob); device_free(v->litCounter);
 	device_free(v->mailbox); device_free(v->barrierStatus);
 	v->peerAttached = false;
 	for(int slot = 0; slot < 2; slot++)
@@ -1199,12 +1199,12 @@ static int light_kernel_choice()
 	if(g_lightKernel < 0)
 	{
 		const char* env = getenv("DN_B200_LIGHT_KERNEL");
-		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : (env && strcmp(env, "flat") == 0) ? 1 : 2;
+		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : (env && strcmp(env, "flat") == 0) ? 1 : (env && strcmp(env, "wave") == 0) ? 3 : 2;
 	}
 	return g_lightKernel;
 }
 
-extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = (which >= 0 && which <= 2) ? which : 2; }
+extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = (which >= 0 && which <= 3) ? which : 2; }
 extern "C" int DN_b200_get_light_kernel(void) { return light_kernel_choice(); }
 
 /* Auto mode.  The two kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a
@@ -1219,7 +1219,7 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 	*slotOut = -1;
 	const int mode = light_kernel_choice();
 	if(mode != 2)
-		return mode;
+		return mode == 3 ? 2 : mode;
 
 	/* harvest finished timings */
 	for(int slot = 0; slot < 2; slot++)
@@ -1242,15 +1242,24 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 
 	int k;
 	const uint64_t n = t.dispatches++;
-	if(t.samples[0] < 2 || t.samples[1] < 2)
-		k = (int)(n & 1u) ^ 1;                     /* flat, warp, flat, warp ... until both have two timings */
+	if(t.samples[0] < 2 || t.samples[1] < 2 || t.samples[2] < 2)
+	{
+		/* round robin over the kernels that still lack two timings (the first dispatch of a volume is never timed) */
+		k = (int)(n % 3u);
+		for(int tries = 0; tries < 3 && t.samples[k] >= 2; tries++)
+			k = (k + 1) % 3;
+	}
 	else
 	{
-		/* hysteresis: the kernel that ran last keeps running unless the other one is at least 5 % faster */
+		/* hysteresis: the kernel that ran last keeps running unless another one is at least 5 % faster */
 		const int last = t.lastKernel;
-		k = t.nsPerCta[last ^ 1] < 0.95 * t.nsPerCta[last] ? (last ^ 1) : last;
+		int best = 0;
+		for(int o = 1; o < 3; o++)
+			if(t.nsPerCta[o] < t.nsPerCta[best])
+				best = o;
+		k = (best != last && t.nsPerCta[best] < 0.95 * t.nsPerCta[last]) ? best : last;
 		if((n & 63u) == 63u)
-			k ^= 1;                                  /* keep the other kernel's estimate fresh */
+			k = (k + 1 + (int)((n >> 6) & 1u)) % 3;  /* keep the other kernels' estimates fresh, in turn */
 		else
 			t.lastKernel = k;
 	}
@@ -1269,6 +1278,24 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 				break;
 			}
 	return k;
+}
+
+/* pool size of the wavefront kernels: every voxel of the dispatch in flight at once when that fits, else the cap set with
+ * DN_b200_set_wave_slots / $DN_B200_WAVE_SLOTS (default 1 Mi slots = 240 MiB; the passes then stream the dispatch through the pool) */
+static uint32_t g_waveSlots = 0;
+extern "C" void DN_b200_set_wave_slots(uint32_t slots)
+{
+	g_waveSlots = slots == 0 ? 0 : (std::min<uint32_t>(std::max<uint32_t>(slots, 128u), 1u << 26) + 127u) & ~127u;
+}
+static uint32_t wave_pool_slots(uint32_t numCtas)
+{
+	if(g_waveSlots == 0)
+	{
+		const char* env = getenv("DN_B200_WAVE_SLOTS");
+		DN_b200_set_wave_slots(env && atoll(env) >= 128 ? (uint32_t)std::min<long long>(atoll(env), 1ll << 26) : (1u << 20));
+	}
+	const unsigned long long items = (unsigned long long)numCtas * 128ull;
+	return (uint32_t)std::min<unsigned long long>(items, g_waveSlots);
 }
 
 static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSamples, float time)
@@ -1377,7 +1404,14 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
 	int timingSlot = -1;
 	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
-	ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
+	if(kernel == 2)
+	{
+		const uint32_t P = wave_pool_slots(numCtas);
+		ok = ok && (P == 0 || device_reserve(v->waveCtx, (size_t)P * (dnb_wave_slot_bytes() / sizeof(uint4)), false, false, "wavefront lighting contexts"));
+		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 12, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
+	}
+	else
+		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
 	if(timingSlot >= 0)
 		cudaEventRecord(v->tuner.end[timingSlot], s);
 	v->tuner.launches[kernel]++;
@@ -1476,7 +1510,7 @@ static bool array_info(VolumeImpl* v, DNb200array which, void** ptr, size_t* byt
 	case DN_B200_STAGING:
 	{
 		*ptr = v->staging.ptr;
-		*bytes = (v->peerAttached ? v->stagedRequests : slice_len(v->stagedRequests, v->shardWorld) * v->shardWorld) * 96 * sizeof(uint32_t);
+		*bytes = (v->peerAttached || v->shardWorld <= 1 ? v->stagedRequests : slice_len(v->stagedRequests, v->shardWorld) * v->shardWorld) * 96 * sizeof(uint32_t);
 		return true;
 	}
 	}
@@ -1574,6 +1608,9 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 	v->stats.lightLaunchesFlat = v->tuner.launches[1];
 	v->stats.nsPerCtaWarp = (float)v->tuner.nsPerCta[0];
 	v->stats.nsPerCtaFlat = (float)v->tuner.nsPerCta[1];
+	v->stats.lightLaunchesWave = v->tuner.launches[2];
+	v->stats.nsPerCtaWave = (float)v->tuner.nsPerCta[2];
+	v->stats.lastWavePasses = v->tuner.lastWavePasses;
 	if(ctx().ready && v->litCounter.ptr && DN_b200_synchronize())
 	{
 		unsigned long long lit = 0;

@@ -86,6 +86,7 @@ struct VolumeImpl
 	DeviceArray<uint32_t>           staging;   /* 96 words per request */
 	DeviceArray<uint32_t>           blockCounts, blockOffsets, scalars;
 	DeviceArray<uint32_t>           forcedList;
+	DeviceArray<uint4>              waveCtx;   /* context pool of the wavefront lighting kernels (light_wave.cuh), allocated on first use */
 	DeviceArray<unsigned long long> litCounter; /* voxel lighting updates committed since creation */
 	DeviceArray<unsigned char>      blob;      /* device side of the upload batch */
 	unsigned char* pinnedBlob = nullptr;
@@ -105,11 +106,12 @@ struct VolumeImpl
 		cudaEvent_t begin[2] = {nullptr, nullptr}, end[2] = {nullptr, nullptr}; /* two timing slots in rotation */
 		int      slotKernel[2] = {-1, -1};   /* kernel timed in each slot, -1 = slot free */
 		uint32_t slotCtas[2] = {0, 0};
-		double   nsPerCta[2] = {0.0, 0.0};    /* running estimate per kernel */
-		uint32_t samples[2] = {0, 0};
+		double   nsPerCta[3] = {0.0, 0.0, 0.0}; /* running estimate per kernel: 0 warp per request, 1 persistent, 2 wavefront */
+		uint32_t samples[3] = {0, 0, 0};
 		uint64_t dispatches = 0;
-		uint64_t launches[2] = {0, 0};
+		uint64_t launches[3] = {0, 0, 0};
 		int      lastKernel = 1;
+		uint32_t lastWavePasses = 0;
 	} tuner;
 
 	/* ---- multi-GPU over peer memory (DoonEngine/b200.h) ---- */

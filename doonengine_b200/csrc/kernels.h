@@ -28,6 +28,12 @@ cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t s
  * state-machine kernel dn_light_flat_kernel (light_flat.cuh).  Both give identical results. */
 cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
                              const DnbStagingTargets* targets, uint32_t* flatCounter, cudaStream_t stream);
+/* the same dispatch as a wavefront over a pool of P context slots in global memory (light_wave.cuh): ctx = dnb_wave_slot_bytes() * P
+ * bytes, P a multiple of 128; counters = 4 device words.  Queues its passes on `stream` and returns once the last voxel is staged
+ * (the host follows the live-slot count a few passes behind); passesOut = passes queued. */
+size_t      dnb_wave_slot_bytes(void);
+cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+                                  const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream);
 /* peers: NULL, or the table whose propagate bitmaps (all replicas') are ORed into visible instead of only the local one */
 cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
                               unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream);

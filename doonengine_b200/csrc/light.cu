@@ -25,6 +25,7 @@
 #include "kernels.h"
 #include "trace.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 /* LI:23 */
 __constant__ float c_spherePoints[15][3] = {
@@ -401,6 +402,7 @@ __global__ void dn_merge_visible_peers_kernel(DnbPeerTable T, uint32_t* __restri
 }
 
 #include "light_flat.cuh"
+#include "light_wave.cuh"
 
 static DnbFlatTuning g_flatTuning = {0, 0, 0};
 

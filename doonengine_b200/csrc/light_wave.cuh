@@ -1,0 +1,375 @@
+/* light_wave.cuh (included at the end of light.cu, after light_flat.cuh whose per-voxel functions it reuses) -- the lighting
+ * update as a WAVEFRONT: the voxel contexts live in global memory and two kernels alternate over a pool of P context slots.
+ *
+ *   dn_wave_serve_kernel   one thread per slot, every lane busy: shade the ray segment that just ended (flat_ray_ended: LI:96-145,
+ *                          174-202, 77-79), advance the voxel's ray schedule, store a finished voxel's three staged words and
+ *                          immediately set the slot up with the next voxel of the dispatch (flat_setup_voxel, LI:207-251), then
+ *                          prepare the next ray segment completely (direction, reciprocal, tile-level DDA start) and store it
+ *   dn_wave_step_kernel    persistent warps; every lane traces one prepared ray segment with the two-state machine TILE / VOX
+ *                          (flat_tile_step / flat_vox_step = trace_ray<false,false>, trace.cuh) and, when its ray ends, stores
+ *                          the result and takes the next slot of its warp's range -- a lane never waits for shading
+ *
+ * Why: in dn_light_flat_kernel (one context per lane, in registers) ncu attributes ~40 % of all issue slots to ray set-up and
+ * shading executed with 2-4 active lanes, and the stepping phases run with 7-9 lanes because half the warp is waiting for that
+ * service (profiles/r2_wave.md).  Moving the contexts to memory costs ~0.3 KB of traffic per ray segment and buys full warps
+ * for shading and twice the lanes for stepping.  Nothing about a voxel's own sequence of operations changes -- the same
+ * functions run in the same order on the same values -- so the staged words are bit-identical to both other kernels
+ * (tests/test_parity_gpu.py runs every lighting test against all three).
+ *
+ * Slot layout: structure of arrays, 15 planes of P uint4 (240 bytes per slot), so that both kernels move whole 16-byte words
+ * and the serve kernel's accesses are fully coalesced.
+ */
+enum : uint32_t
+{
+	WV_REC = 0,   /* the voxel's record */
+	WV_ORG = 1,   /* origin.xyz, indirectSamples */
+	WV_SPEC = 2,  /* spec.xyz, work item index */
+	WV_DIFF = 3,  /* diff.xyz, schedule word (WS_*) */
+	WV_PA = 4,    /* pa.xyz */
+	WV_PB = 5,    /* pb.xyz */
+	WR_DIR = 6,   /* ray: dir.xyz, lastVoxID */
+	WR_POS = 7,   /* ray: origin of the segment, lastVoxRefract */
+	WR_INV = 8,   /* ray: 1/dir, flags (WF_READY | WF_TRIPPED) */
+	WR_SIDE = 9,  /* ray: tile-level sideDist */
+	WR_CELL = 10, /* ray: tile-level cell (int) */
+	WH_POS = 11,  /* result: hit position (or the origin), flags (WF_HIT | WF_TRIPPED | WF_INSIDE) */
+	WH_COL = 12,  /* result: colorAdd.xyz, colorMult */
+	WH_VOX = 13,  /* result: record hit (written / read only on a hit) */
+	WH_ST = 14,   /* result: lastVoxID, lastVoxRefract (written / read only with WF_INSIDE) */
+	WAVE_PLANES = 15
+};
+enum : uint32_t { WF_READY = 1u, WF_TRIPPED = 2u, WF_HIT = 1u, WF_INSIDE = 4u };
+/* schedule word: kind[0:2) idx[2:8) seg[8:16) firstSample[16] sourceVisible[17] reflectType[18:26) active[31] */
+#define WS_ACTIVE 0x80000000u
+
+DNB_FN uint4 f3w(f3 a, uint32_t w) { return make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), w); }
+DNB_FN f3 xyz_of(uint4 v) { return mk3(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)); }
+
+__global__ void __launch_bounds__(128) dn_wave_serve_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
+                                                            uint32_t* __restrict__ workCounter, DnbStagingTargets T, uint4* __restrict__ ctx, uint32_t P, uint32_t* __restrict__ activeNow,
+                                                            uint32_t* __restrict__ activeNext)
+{
+	const uint32_t i = blockIdx.x * 128u + threadIdx.x; /* the grid covers the pool exactly (P is a multiple of 128) */
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	if(i == 0)
+	{
+		*activeNext = 0;     /* the counter the NEXT pass adds to (stream order keeps the passes apart) */
+		workCounter[3] = 0;  /* slot cursor of the step kernel that follows this pass */
+	}
+#define PL(p) ctx[(size_t)(p) * P + i]
+
+	FlatLane L;
+	uint32_t state = ST_FETCH, item = 0;
+	bool start = false;
+
+	const uint4 vDiff = PL(WV_DIFF);
+	if(vDiff.w & WS_ACTIVE)
+	{
+		const uint32_t sched = vDiff.w;
+		const uint4 vRec = PL(WV_REC), vOrg = PL(WV_ORG), vSpec = PL(WV_SPEC), vPa = PL(WV_PA), vPb = PL(WV_PB), rDir = PL(WR_DIR), hPos = PL(WH_POS), hCol = PL(WH_COL);
+		L.rec = vRec;
+		L.origin = xyz_of(vOrg);
+		L.indirectSamples = __uint_as_float(vOrg.w);
+		L.spec = xyz_of(vSpec);
+		item = vSpec.w;
+		L.diff = xyz_of(vDiff);
+		L.kind = sched & 3u;
+		L.idx = (sched >> 2) & 63u;
+		L.seg = (sched >> 8) & 255u;
+		L.firstSample = (sched >> 16) & 1u;
+		L.sourceVisible = (sched >> 17) & 1u;
+		L.reflectType = (sched >> 18) & 255u;
+		L.pa = xyz_of(vPa);
+		L.pb = xyz_of(vPb);
+		L.dir = xyz_of(rDir);
+		L.pos = xyz_of(hPos);
+		L.hit = hPos.w & WF_HIT;
+		L.colorAdd = xyz_of(hCol);
+		L.colorMult = __uint_as_float(hCol.w);
+		L.st.tripped = (hPos.w & WF_TRIPPED) != 0u;
+		L.st.lastVoxID = 255u;
+		L.st.lastVoxRefract = 1.0f;
+		L.st.vox = make_uint4(0, 0, 0, 0);
+		L.st.hitMapIndex = L.st.hitLocalIndex = L.st.hitRecord = 0;
+		if(L.hit)
+			L.st.vox = PL(WH_VOX);
+		if(hPos.w & WF_INSIDE)
+		{
+			const uint4 hSt = PL(WH_ST);
+			L.st.lastVoxID = hSt.x;
+			L.st.lastVoxRefract = __uint_as_float(hSt.y);
+		}
+		const uint32_t r = (firstCta + (item >> 7) * ctaStride) * 4u + ((item >> 5) & 3u);
+		L.at = (size_t)r * 96u + (item & 31u);
+		state = ST_END;
+		start = flat_ray_ended(S, T, L, state); /* false + ST_FETCH: the voxel is finished and its words are staged */
+	}
+
+	/* free slots take the next voxels of the dispatch (two rounds: an item can turn out to hold no voxel) */
+#pragma unroll 1
+	for(int round = 0; round < 2; round++)
+	{
+		const uint32_t mF = __ballot_sync(0xFFFFFFFFu, state == ST_FETCH);
+		if(mF == 0u)
+			break;
+		uint32_t base = 0;
+		const int leader = __ffs(mF) - 1;
+		if((int)lane == leader)
+		{
+			base = *reinterpret_cast<volatile uint32_t*>(workCounter);
+			if(base < totalItems) /* once the list is exhausted the counter stops moving (it would wrap after 2^32 idle passes otherwise) */
+				base = atomicAdd(workCounter, (uint32_t)__popc(mF));
+		}
+		base = __shfl_sync(0xFFFFFFFFu, base, leader);
+		if(state == ST_FETCH)
+		{
+			const uint32_t j = base + (uint32_t)__popc(mF & ltMask);
+			if(j < totalItems)
+			{
+				item = j;
+				start = flat_setup_voxel(S, T, requests, numRequests, firstCta, ctaStride, j, L, state);
+			}
+			else
+				state = ST_DONE;
+		}
+	}
+
+	if(start)
+	{
+		/* flat_start_ray, with its result stored instead of kept */
+		const f3 inv = rcp3(L.dir);
+		Dda m;
+		init_dda(L.dir, inv, L.pos, m);
+		PL(WV_REC) = L.rec;
+		PL(WV_ORG) = f3w(L.origin, __float_as_uint(L.indirectSamples));
+		PL(WV_SPEC) = f3w(L.spec, item);
+		PL(WV_DIFF) = f3w(L.diff, WS_ACTIVE | (L.kind & 3u) | ((L.idx & 63u) << 2) | ((L.seg & 255u) << 8) | (L.firstSample ? 1u << 16 : 0u) | (L.sourceVisible ? 1u << 17 : 0u) | ((L.reflectType & 255u) << 18));
+		PL(WV_PA) = f3w(L.pa, 0);
+		PL(WV_PB) = f3w(L.pb, 0);
+		PL(WR_DIR) = f3w(L.dir, L.st.lastVoxID);
+		PL(WR_POS) = f3w(L.pos, __float_as_uint(L.st.lastVoxRefract));
+		PL(WR_INV) = f3w(inv, WF_READY | (L.st.tripped ? WF_TRIPPED : 0u));
+		PL(WR_SIDE) = f3w(m.side, 0);
+		PL(WR_CELL) = make_uint4((uint32_t)m.pos.x, (uint32_t)m.pos.y, (uint32_t)m.pos.z, 0);
+	}
+	else
+	{
+		if(vDiff.w & WS_ACTIVE)
+			PL(WV_DIFF) = make_uint4(0, 0, 0, 0);
+		PL(WR_INV) = make_uint4(0, 0, 0, 0);
+	}
+#undef PL
+
+	const uint32_t mA = __ballot_sync(0xFFFFFFFFu, start);
+	if(lane == 0 && mA)
+		atomicAdd(activeNow, (uint32_t)__popc(mA));
+}
+
+#ifndef WAVE_MIN_BLOCKS
+#define WAVE_MIN_BLOCKS 5
+#endif
+#define WAVE_GRAB 64u /* slots a warp takes from the pass's cursor at a time */
+__global__ void __launch_bounds__(128, WAVE_MIN_BLOCKS) dn_wave_step_kernel(DnbScene S, uint4* __restrict__ ctx, uint32_t P, uint32_t* __restrict__ cursor, DnbFlatTuning K)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	/* the warp's current range of slots; ranges are handed out dynamically so that no warp is left with a long tail */
+	uint32_t next = 0, end = 0;
+	bool exhausted = false;
+
+	FlatLane L;
+	uint32_t state = ST_FETCH, slot = 0;
+	L.hit = false;
+	int waited = 0;
+
+	for(;;)
+	{
+		const uint32_t mT = __ballot_sync(0xFFFFFFFFu, state == ST_TILE);
+		const uint32_t mV = __ballot_sync(0xFFFFFFFFu, state == ST_VOX);
+		const int nT = __popc(mT), nV = __popc(mV), nF = 32 - nT - nV;
+		if(next >= end && !exhausted && (nF >= K.endLanes || nT + nV == 0))
+		{
+			uint32_t base = 0;
+			if(lane == 0)
+				base = atomicAdd(cursor, WAVE_GRAB);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if(base < P)
+			{
+				next = base;
+				end = base + WAVE_GRAB < P ? base + WAVE_GRAB : P;
+			}
+			else
+				exhausted = true;
+		}
+		if(nT + nV == 0 && next >= end)
+		{
+			if(exhausted)
+				break;
+			continue;
+		}
+
+		if(next < end && (nF >= K.endLanes || nT + nV == 0 || (nF > 0 && waited >= K.patience)))
+		{
+			/* idle lanes take the next slots of this warp's range */
+			waited = 0;
+			const uint32_t mF = ~(mT | mV);
+			if(state == ST_FETCH)
+			{
+				const uint32_t idx = next + (uint32_t)__popc(mF & ltMask);
+				if(idx < end)
+				{
+					const uint4 rInv = ctx[(size_t)WR_INV * P + idx];
+					if(rInv.w & WF_READY)
+					{
+						const uint4 rDir = ctx[(size_t)WR_DIR * P + idx], rPos = ctx[(size_t)WR_POS * P + idx], rSide = ctx[(size_t)WR_SIDE * P + idx], rCell = ctx[(size_t)WR_CELL * P + idx];
+						slot = idx;
+						L.dir = xyz_of(rDir);
+						L.inv = xyz_of(rInv);
+						L.pos = xyz_of(rPos);
+						L.st.lastVoxID = rDir.w;
+						L.st.lastVoxRefract = __uint_as_float(rPos.w);
+						L.st.tripped = (rInv.w & WF_TRIPPED) != 0u;
+						L.st.vox = make_uint4(0, 0, 0, 0);
+						L.m.pos.x = (int)rCell.x; L.m.pos.y = (int)rCell.y; L.m.pos.z = (int)rCell.z;
+						L.m.side = xyz_of(rSide);
+						L.m.delta = abs3(L.inv);
+						L.m.step.x = isgn(L.dir.x); L.m.step.y = isgn(L.dir.y); L.m.step.z = isgn(L.dir.z);
+						L.colorAdd = splat3(0.0f);
+						L.colorMult = 1.0f;
+						L.tLast = 0.0f;
+						L.ignoreFirst = true;
+						L.guard = 0;
+						L.blk.x = L.blk.y = L.blk.z = 0x40000000;
+						L.occWord = 0;
+						L.hit = false;
+						state = ST_TILE;
+					}
+				}
+			}
+			next += (uint32_t)nF;
+			continue;
+		}
+
+		if(nT >= nV)
+		{
+			const int keep = (3 * nT + 3) >> 2;
+#pragma unroll 1
+			for(int it = 0; it < K.budget; it++)
+			{
+				if(state == ST_TILE)
+					flat_tile_step(S, L, state);
+				waited++;
+				if(__popc(__ballot_sync(0xFFFFFFFFu, state == ST_TILE)) < keep)
+					break;
+			}
+		}
+		else
+		{
+			const int keep = (3 * nV + 3) >> 2;
+#pragma unroll 1
+			for(int it = 0; it < K.budget; it++)
+			{
+				if(state == ST_VOX)
+					flat_vox_step(S, L, state);
+				waited++;
+				if(__popc(__ballot_sync(0xFFFFFFFFu, state == ST_VOX)) < keep)
+					break;
+			}
+		}
+
+		if(state == ST_END)
+		{
+			/* the segment is over: its result goes back to the slot, the lane is free */
+			const bool inside = L.st.lastVoxID != 255u;
+			ctx[(size_t)WH_POS * P + slot] = f3w(L.pos, (L.hit ? WF_HIT : 0u) | (L.st.tripped ? WF_TRIPPED : 0u) | (inside ? WF_INSIDE : 0u));
+			ctx[(size_t)WH_COL * P + slot] = f3w(L.colorAdd, __float_as_uint(L.colorMult));
+			if(L.hit)
+				ctx[(size_t)WH_VOX * P + slot] = L.st.vox;
+			if(inside)
+				ctx[(size_t)WH_ST * P + slot] = make_uint4(L.st.lastVoxID, __float_as_uint(L.st.lastVoxRefract), 0, 0);
+			state = ST_FETCH;
+		}
+	}
+}
+
+/* host side of one wavefront dispatch.  Passes are queued without waiting; every pass copies its count of live slots to a
+ * pinned ring and the host looks at the count of the pass WAVE_LAG passes back before queueing another, so the device never
+ * runs dry and at most WAVE_LAG empty passes are queued after the last voxel has finished. */
+#define WAVE_LAG 3
+struct DnbWaveHost
+{
+	uint32_t*   pinned = nullptr; /* ring of 8 counts */
+	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	int         stepCtas = 0;
+};
+static DnbWaveHost g_wave;
+
+extern "C" size_t dnb_wave_slot_bytes(void) { return (size_t)WAVE_PLANES * sizeof(uint4); }
+
+/* ctx: WAVE_PLANES * P uint4; counters: 4 device words (work counter, two live-slot counters, spare) */
+extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+                                             const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream)
+{
+	if(passesOut)
+		*passesOut = 0;
+	if(numRequests == 0 || numCtas == 0 || P == 0)
+		return cudaSuccess;
+	cudaError_t e;
+	if(!g_wave.pinned)
+	{
+		if((e = cudaMallocHost((void**)&g_wave.pinned, 8 * sizeof(uint32_t))) != cudaSuccess)
+			return e;
+		for(int i = 0; i < 8; i++)
+			if((e = cudaEventCreateWithFlags(&g_wave.ev[i], cudaEventDisableTiming)) != cudaSuccess)
+				return e;
+		int dev = 0, sms = 148, perSm = WAVE_MIN_BLOCKS;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dn_wave_step_kernel, 128, 0) != cudaSuccess || perSm < 1)
+			perSm = WAVE_MIN_BLOCKS;
+		g_wave.stepCtas = sms * perSm;
+	}
+	DnbFlatTuning tuning;
+	{
+		auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v && atoi(v) > 0 ? atoi(v) : dflt; };
+		tuning.budget = knob("DN_B200_WAVE_BUDGET", 24);
+		tuning.endLanes = knob("DN_B200_WAVE_FETCH", 8);
+		tuning.patience = knob("DN_B200_WAVE_PATIENCE", 4);
+	}
+
+	/* every slot idle, counters zero */
+	if((e = cudaMemsetAsync(ctx + (size_t)WV_DIFF * P, 0, (size_t)P * sizeof(uint4), stream)) != cudaSuccess)
+		return e;
+	if((e = cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), stream)) != cudaSuccess)
+		return e;
+
+	const uint32_t totalItems = numCtas * 128u;
+	const uint32_t stepCtas = std::min<uint32_t>((uint32_t)g_wave.stepCtas, (P + 4u * WAVE_GRAB - 1u) / (4u * WAVE_GRAB));
+
+	uint32_t pass = 0;
+	for(;; pass++)
+	{
+		if(pass >= WAVE_LAG)
+		{
+			const uint32_t look = pass - WAVE_LAG;
+			if((e = cudaEventSynchronize(g_wave.ev[look & 7u])) != cudaSuccess)
+				return e;
+			if(g_wave.pinned[look & 7u] == 0u)
+				break; /* that pass left no live slot: every voxel of the dispatch is staged */
+		}
+		uint32_t* now = counters + 1 + (pass & 1u);
+		uint32_t* nxt = counters + 1 + ((pass + 1u) & 1u);
+		dn_wave_serve_kernel<<<P / 128u, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, totalItems, counters, *targets, ctx, P, now, nxt);
+		if((e = cudaMemcpyAsync(&g_wave.pinned[pass & 7u], now, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+			return e;
+		if((e = cudaEventRecord(g_wave.ev[pass & 7u], stream)) != cudaSuccess)
+			return e;
+		dn_wave_step_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters + 3, tuning);
+		if((e = cudaGetLastError()) != cudaSuccess)
+			return e;
+	}
+	if(passesOut)
+		*passesOut = pass;
+	return cudaSuccess;
+}

@@ -49,10 +49,15 @@ bool DN_b200_read_hits(GLuint fb, DNb200hit* dst, size_t count);
 
 /* ---- lighting kernel choice: 0 = one warp per lighting request (the reference's work-group shape, voxel.c:950 / LI:3),
  * 1 = persistent warps running every voxel as a state machine with dynamic work fetch (same results bit for bit),
- * 2 = auto (default): both are timed on live dispatches of this volume and the faster one runs.
- * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat" | "auto". ---- */
+ * 3 = wavefront: voxel contexts in device memory, a full-warp shading / ray set-up kernel alternating with a persistent
+ *     ray-stepping kernel (same results bit for bit; fastest on large maps with rays of very different length),
+ * 2 = auto (default): all three are timed on live dispatches of this volume and the fastest one runs.
+ * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat" | "wave" | "auto". ---- */
 void DN_b200_set_light_kernel(int which);
 int  DN_b200_get_light_kernel(void);
+/* context-pool size of the wavefront kernels (rounded to a multiple of 128; 0 = default / $DN_B200_WAVE_SLOTS = 1 Mi slots of 240
+ * bytes).  A dispatch with more voxels than slots is streamed through the pool; results do not depend on the size. */
+void DN_b200_set_wave_slots(uint32_t slots);
 /* scheduling knobs of the persistent kernel (see csrc/light_flat.cuh); results do not depend on them.  0 = defaults / environment */
 void DN_b200_set_flat_tuning(int budget, int endLanes, int patience);
 
@@ -91,6 +96,9 @@ typedef struct DNb200stats
 	uint64_t lightLaunchesWarp, lightLaunchesFlat;          /* lighting dispatches run by each kernel */
 	float    nsPerCtaWarp, nsPerCtaFlat;                    /* auto mode: running estimate of each kernel's time per 4 requests */
 	float    lastScanHostMs, lastPackHostMs, lastEnqueueHostMs; /* host wall-clock of the last writing sync: dirty-tile scan + sort, packing, allocation + enqueue */
+	uint64_t lightLaunchesWave;                             /* lighting dispatches run by the wavefront kernels */
+	float    nsPerCtaWave;                                  /* auto mode: their time per 4 requests */
+	uint32_t lastWavePasses;                                /* serve + step passes the last wavefront dispatch queued */
 } DNb200stats;
 void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
 void DN_b200_enable_timing(bool enable); /* record CUDA events around each kernel group (adds a sync when read) */

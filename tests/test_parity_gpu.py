@@ -18,11 +18,11 @@ pytestmark = pytest.mark.gpu
 W, H, FRAMES = 320, 192, 4
 
 
-@pytest.fixture(autouse=True, params=["flat", "warp"])
+@pytest.fixture(autouse=True, params=["flat", "warp", "wave"])
 def light_kernel(request, dn):
-    """every test of this module runs against both lighting kernels: the persistent state machine (light_flat.cuh, the
-    default) and the one-warp-per-request kernel (light.cu); their results must be the same bits."""
-    dn.lib().DN_b200_set_light_kernel(1 if request.param == "flat" else 0)
+    """every test of this module runs against all three lighting kernels: the persistent state machine (light_flat.cuh), the
+    one-warp-per-request kernel (light.cu) and the wavefront pair (light_wave.cuh); their results must be the same bits."""
+    dn.lib().DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3}[request.param])
     yield request.param
     dn.lib().DN_b200_set_light_kernel(2)  # back to auto
 
@@ -484,4 +484,39 @@ def test_lighting_checkpoint_round_trip(dn, tmp_path):
     sc = records_by_tile(c)
     assert int(sc["samples"][0]) == 0 and np.array_equal(sc["samples"][1:], snap["samples"][1:])
     for e in (a, b, c):
+        e.close()
+
+
+def test_kernels_agree_on_sparse_map_with_streamed_pool(dn, light_kernel):
+    """the three lighting kernels stage the same words on a sparse map (long rays of very different length, glossy and emissive balls),
+    with the wavefront context pool far smaller than the dispatch so that slots are refilled pass after pass, and at several pool sizes.
+    Runs once (under the "warp" parametrisation): it drives all kernels itself."""
+    if light_kernel != "warp":
+        pytest.skip("drives every kernel itself")
+    from doonengine_b200 import scenes
+    L = dn.lib()
+    tiles = (20, 20, 20)
+    e = dn.Engine(map_size=tiles, min_chunks=scenes.native_count("sparse", tiles) + 16)
+    scenes.build_native(e, "sparse", tiles, **scenes.sparse_camera(tiles))
+    e.sync(1, 1)
+    try:
+        for k in range(3):
+            e.draw(640, 368)
+            e.sync(2, 1)
+            n = e.num_requests()
+            assert n > 2000
+            staged = {}
+            for name, mode, slots in (("warp", 0, 0), ("flat", 1, 0), ("wave-all", 3, 1 << 22), ("wave-4k", 3, 4096), ("wave-640", 3, 640)):
+                L.DN_b200_set_light_kernel(mode)
+                if mode == 3:
+                    L.DN_b200_set_wave_slots(slots)
+                assert L.DN_b200_light_compute(e.vol, 1, 1000, 1.0 + k / 60.0)
+                staged[name] = e.download(dn.ARRAY_STAGING, np.uint32)[:n * 96].copy()
+            for name, words in staged.items():
+                assert np.array_equal(words, staged["warp"]), "frame %d: %s differs from the warp-per-request kernel in %d words" % (k, name, int((words != staged["warp"]).sum()))
+            assert staged["warp"].any()
+            assert L.DN_b200_light_commit(e.vol)
+    finally:
+        L.DN_b200_set_wave_slots(0)
+        L.DN_b200_set_light_kernel(2)
         e.close()

@@ -1,5 +1,5 @@
 """A/B of the lighting kernels and of the persistent kernel's scheduling knobs on one scene (run on the GPU box).
-usage: python tools/light_sweep.py c2|c3s|c5s [frames]"""
+usage: [DN_B200_WAVE_SLOTS=.. DN_B200_WAVE_FETCH=.. ...] python tools/light_sweep.py c2|c3s|c5s [frames] [warp,flat,wave]"""
 import json
 import os
 import sys
@@ -20,18 +20,25 @@ dn.init(0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 L.DN_b200_set_stream(stream.cuda_stream)
-chunks, camera = bench.make_chunks(scene, tiles) if scene != "demo" else ([], {})
-e = bench.build_engine(dn.Engine, scene, tiles, chunks, camera)
+if scene in ("sparse", "dense"):
+    from doonengine_b200 import scenes
+    camera = scenes.sparse_camera(tiles) if scene == "sparse" else scenes.dense_camera(tiles)
+    e = dn.Engine(map_size=tiles, min_chunks=scenes.native_count(scene, tiles) + 16)
+    scenes.build_native(e, scene, tiles, **camera)
+else:
+    chunks, camera = bench.make_chunks(scene, tiles) if scene != "demo" else ([], {})
+    e = bench.build_engine(dn.Engine, scene, tiles, chunks, camera)
 e.sync(dn.DN_WRITE, 1)
 fb = e.framebuffer(w, h)
 view, proj = e.view_projection(h / w)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-variants = [("warp", None), ("flat", (24, 28, 16))]
+names = sys.argv[3].split(",") if len(sys.argv) > 3 else ["warp", "flat", "wave"]
+variants = [(n, (24, 28, 16) if n == "flat" else None) for n in names]
 out = []
 k = 0
 for name, knobs in variants:
-    L.DN_b200_set_light_kernel(1 if name == "flat" else 0)
+    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3}[name])
     if knobs:
         L.DN_b200_set_flat_tuning(*knobs)
     times, dtimes = [], []
@@ -53,6 +60,6 @@ for name, knobs in variants:
         if f >= 2:
             times.append(a.elapsed_time(b))
             dtimes.append(d0.elapsed_time(d1))
-    rec = {"config": cfg, "kernel": name, "knobs": knobs, "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "draw_ms_median": float(np.median(dtimes)), "requests": int(e.vol.contents.numLightingRequests)}
+    rec = {"config": cfg, "kernel": name, "knobs": knobs, "env": {k: v for k, v in os.environ.items() if k.startswith("DN_B200_")}, "wave_passes": int(e.stats()["lastWavePasses"]), "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "draw_ms_median": float(np.median(dtimes)), "requests": int(e.vol.contents.numLightingRequests)}
     print(json.dumps(rec), flush=True)
     out.append(rec)
