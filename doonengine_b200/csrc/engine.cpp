@@ -1285,7 +1285,7 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 static uint32_t g_waveSlots = 0;
 extern "C" void DN_b200_set_wave_slots(uint32_t slots)
 {
-	g_waveSlots = slots == 0 ? 0 : (std::min<uint32_t>(std::max<uint32_t>(slots, 128u), 1u << 26) + 127u) & ~127u;
+	g_waveSlots = slots == 0 ? 0 : (std::min<uint32_t>(std::max<uint32_t>(slots, 256u), 1u << 26) + 255u) & ~255u;
 }
 static uint32_t wave_pool_slots(uint32_t numCtas)
 {
@@ -1294,7 +1294,7 @@ static uint32_t wave_pool_slots(uint32_t numCtas)
 		const char* env = getenv("DN_B200_WAVE_SLOTS");
 		DN_b200_set_wave_slots(env && atoll(env) >= 128 ? (uint32_t)std::min<long long>(atoll(env), 1ll << 26) : (1u << 20));
 	}
-	const unsigned long long items = (unsigned long long)numCtas * 128ull;
+	const unsigned long long items = ((unsigned long long)numCtas * 128ull + 255ull) & ~255ull; /* the serve kernel's CTAs hold 256 slots */
 	return (uint32_t)std::min<unsigned long long>(items, g_waveSlots);
 }
 

@@ -24,8 +24,10 @@
  */
 #include "kernels.h"
 #include "trace.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <cuda_pipeline.h>
 
 /* LI:23 */
 __constant__ float c_spherePoints[15][3] = {

@@ -45,11 +45,13 @@ enum : uint32_t { WF_READY = 1u, WF_TRIPPED = 2u, WF_HIT = 1u, WF_INSIDE = 4u };
 DNB_FN uint4 f3w(f3 a, uint32_t w) { return make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), w); }
 DNB_FN f3 xyz_of(uint4 v) { return mk3(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)); }
 
-__global__ void __launch_bounds__(128) dn_wave_serve_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
+#define WAVE_SERVE_THREADS 256
+__global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
                                                             uint32_t* __restrict__ workCounter, DnbStagingTargets T, uint4* __restrict__ ctx, uint32_t P, uint32_t* __restrict__ activeNow,
                                                             uint32_t* __restrict__ activeNext)
 {
-	const uint32_t i = blockIdx.x * 128u + threadIdx.x; /* the grid covers the pool exactly (P is a multiple of 128) */
+	__shared__ uint32_t s_warpCount[WAVE_SERVE_THREADS / 32], s_base;
+	const uint32_t i = blockIdx.x * WAVE_SERVE_THREADS + threadIdx.x; /* the grid covers the pool exactly (P is a multiple of 256) */
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t ltMask = (1u << lane) - 1u;
 	if(i == 0)
@@ -106,25 +108,36 @@ __global__ void __launch_bounds__(128) dn_wave_serve_kernel(DnbScene S, const ui
 		start = flat_ray_ended(S, T, L, state); /* false + ST_FETCH: the voxel is finished and its words are staged */
 	}
 
-	/* free slots take the next voxels of the dispatch (two rounds: an item can turn out to hold no voxel) */
+	/* free slots take the next voxels of the dispatch (two rounds: an item can turn out to hold no voxel).  ONE atomic per CTA
+	 * and round: with one per warp the 10^5 same-address atomics of a pass were a quarter of the kernel's stall samples */
 #pragma unroll 1
 	for(int round = 0; round < 2; round++)
 	{
 		const uint32_t mF = __ballot_sync(0xFFFFFFFFu, state == ST_FETCH);
-		if(mF == 0u)
-			break;
-		uint32_t base = 0;
-		const int leader = __ffs(mF) - 1;
-		if((int)lane == leader)
+		if(lane == 0)
+			s_warpCount[threadIdx.x >> 5] = (uint32_t)__popc(mF);
+		__syncthreads();
+		uint32_t before = 0, total = 0;
+#pragma unroll
+		for(uint32_t w = 0; w < WAVE_SERVE_THREADS / 32; w++)
 		{
-			base = *reinterpret_cast<volatile uint32_t*>(workCounter);
-			if(base < totalItems) /* once the list is exhausted the counter stops moving (it would wrap after 2^32 idle passes otherwise) */
-				base = atomicAdd(workCounter, (uint32_t)__popc(mF));
+			const uint32_t c = s_warpCount[w];
+			before += w < (threadIdx.x >> 5) ? c : 0u;
+			total += c;
 		}
-		base = __shfl_sync(0xFFFFFFFFu, base, leader);
+		if(total == 0u)
+			break; /* uniform over the CTA */
+		if(threadIdx.x == 0)
+		{
+			uint32_t base = *reinterpret_cast<volatile uint32_t*>(workCounter);
+			if(base < totalItems) /* once the list is exhausted the counter stops moving (it would wrap after 2^32 idle passes otherwise) */
+				base = atomicAdd(workCounter, total);
+			s_base = base;
+		}
+		__syncthreads();
 		if(state == ST_FETCH)
 		{
-			const uint32_t j = base + (uint32_t)__popc(mF & ltMask);
+			const uint32_t j = s_base + before + (uint32_t)__popc(mF & ltMask);
 			if(j < totalItems)
 			{
 				item = j;
@@ -133,6 +146,7 @@ __global__ void __launch_bounds__(128) dn_wave_serve_kernel(DnbScene S, const ui
 			else
 				state = ST_DONE;
 		}
+		__syncthreads(); /* s_warpCount / s_base are rewritten by the next round */
 	}
 
 	if(start)
@@ -153,10 +167,10 @@ __global__ void __launch_bounds__(128) dn_wave_serve_kernel(DnbScene S, const ui
 		PL(WR_SIDE) = f3w(m.side, 0);
 		PL(WR_CELL) = make_uint4((uint32_t)m.pos.x, (uint32_t)m.pos.y, (uint32_t)m.pos.z, 0);
 	}
-	else
+	else if(vDiff.w & WS_ACTIVE)
 	{
-		if(vDiff.w & WS_ACTIVE)
-			PL(WV_DIFF) = make_uint4(0, 0, 0, 0);
+		/* the slot goes idle (an idle slot stays as it is: both words are already zero) */
+		PL(WV_DIFF) = make_uint4(0, 0, 0, 0);
 		PL(WR_INV) = make_uint4(0, 0, 0, 0);
 	}
 #undef PL
@@ -167,112 +181,138 @@ __global__ void __launch_bounds__(128) dn_wave_serve_kernel(DnbScene S, const ui
 }
 
 #ifndef WAVE_MIN_BLOCKS
-#define WAVE_MIN_BLOCKS 5
+#define WAVE_MIN_BLOCKS 6
 #endif
-#define WAVE_GRAB 64u /* slots a warp takes from the pass's cursor at a time */
+#define WAVE_GRAB 32u /* slots a warp takes from the pass's cursor at a time: one per lane */
+
+/* the five ray planes of 32 consecutive slots -> one of the warp's two shared-memory buffers (cp.async, 16 bytes per lane and plane:
+ * each plane row is one fully coalesced 512-byte read); slots past the end of the pool read slot P-1 again and are never used */
+DNB_FN void wave_prefetch(uint4* __restrict__ buf, const uint4* __restrict__ ctx, uint32_t P, uint32_t base, uint32_t lane)
+{
+	const uint32_t idx = base + lane < P ? base + lane : P - 1u;
+#pragma unroll
+	for(uint32_t p = 0; p < 5u; p++)
+		__pipeline_memcpy_async(buf + p * 32u + lane, ctx + (size_t)(WR_DIR + p) * P + idx, sizeof(uint4));
+	__pipeline_commit();
+}
+
 __global__ void __launch_bounds__(128, WAVE_MIN_BLOCKS) dn_wave_step_kernel(DnbScene S, uint4* __restrict__ ctx, uint32_t P, uint32_t* __restrict__ cursor, DnbFlatTuning K)
 {
-	const uint32_t lane = threadIdx.x & 31u;
+	/* per warp: two buffers of 32 slots x 5 ray planes (2 x 2.5 KB); while the lanes work through one range of slots the next one is
+	 * already on its way, so handing an idle lane its next ray costs five shared-memory reads instead of a round trip to HBM */
+	__shared__ uint4 s_rays[4][2][5 * 32];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t ltMask = (1u << lane) - 1u;
-	/* the warp's current range of slots; ranges are handed out dynamically so that no warp is left with a long tail */
-	uint32_t next = 0, end = 0;
-	bool exhausted = false;
+
+	/* current range [next, end) lives in buffer `cur`; `preBase` (if < P) is the range in flight into the other buffer */
+	uint32_t cur = 0, next = 0, end = 0, preBase = 0xFFFFFFFFu;
+	{
+		uint32_t base = 0;
+		if(lane == 0)
+			base = atomicAdd(cursor, WAVE_GRAB);
+		preBase = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if(preBase >= P)
+			return;
+		wave_prefetch(s_rays[warp][1], ctx, P, preBase, lane);
+	}
 
 	FlatLane L;
 	uint32_t state = ST_FETCH, slot = 0;
 	L.hit = false;
-	int waited = 0;
 
 	for(;;)
 	{
 		const uint32_t mT = __ballot_sync(0xFFFFFFFFu, state == ST_TILE);
 		const uint32_t mV = __ballot_sync(0xFFFFFFFFu, state == ST_VOX);
 		const int nT = __popc(mT), nV = __popc(mV), nF = 32 - nT - nV;
-		if(next >= end && !exhausted && (nF >= K.endLanes || nT + nV == 0))
-		{
-			uint32_t base = 0;
-			if(lane == 0)
-				base = atomicAdd(cursor, WAVE_GRAB);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if(base < P)
-			{
-				next = base;
-				end = base + WAVE_GRAB < P ? base + WAVE_GRAB : P;
-			}
-			else
-				exhausted = true;
-		}
-		if(nT + nV == 0 && next >= end)
-		{
-			if(exhausted)
-				break;
-			continue;
-		}
 
-		if(next < end && (nF >= K.endLanes || nT + nV == 0 || (nF > 0 && waited >= K.patience)))
+		if(nF > 0)
 		{
-			/* idle lanes take the next slots of this warp's range */
-			waited = 0;
-			const uint32_t mF = ~(mT | mV);
-			if(state == ST_FETCH)
+			if(next >= end && preBase < P)
 			{
-				const uint32_t idx = next + (uint32_t)__popc(mF & ltMask);
-				if(idx < end)
+				/* switch to the prefetched range and start fetching the one after it */
+				__pipeline_wait_prior(0);
+				__syncwarp();
+				cur ^= 1u;
+				next = preBase;
+				end = preBase + WAVE_GRAB < P ? preBase + WAVE_GRAB : P;
+				uint32_t base = 0;
+				if(lane == 0)
+					base = atomicAdd(cursor, WAVE_GRAB);
+				preBase = __shfl_sync(0xFFFFFFFFu, base, 0);
+				if(preBase < P)
+					wave_prefetch(s_rays[warp][cur ^ 1u], ctx, P, preBase, lane);
+			}
+			if(next < end)
+			{
+				/* idle lanes take the next slots of the range */
+				const uint32_t mF = ~(mT | mV);
+				if(state == ST_FETCH)
 				{
-					const uint4 rInv = ctx[(size_t)WR_INV * P + idx];
-					if(rInv.w & WF_READY)
+					const uint32_t idx = next + (uint32_t)__popc(mF & ltMask);
+					if(idx < end)
 					{
-						const uint4 rDir = ctx[(size_t)WR_DIR * P + idx], rPos = ctx[(size_t)WR_POS * P + idx], rSide = ctx[(size_t)WR_SIDE * P + idx], rCell = ctx[(size_t)WR_CELL * P + idx];
-						slot = idx;
-						L.dir = xyz_of(rDir);
-						L.inv = xyz_of(rInv);
-						L.pos = xyz_of(rPos);
-						L.st.lastVoxID = rDir.w;
-						L.st.lastVoxRefract = __uint_as_float(rPos.w);
-						L.st.tripped = (rInv.w & WF_TRIPPED) != 0u;
-						L.st.vox = make_uint4(0, 0, 0, 0);
-						L.m.pos.x = (int)rCell.x; L.m.pos.y = (int)rCell.y; L.m.pos.z = (int)rCell.z;
-						L.m.side = xyz_of(rSide);
-						L.m.delta = abs3(L.inv);
-						L.m.step.x = isgn(L.dir.x); L.m.step.y = isgn(L.dir.y); L.m.step.z = isgn(L.dir.z);
-						L.colorAdd = splat3(0.0f);
-						L.colorMult = 1.0f;
-						L.tLast = 0.0f;
-						L.ignoreFirst = true;
-						L.guard = 0;
-						L.blk.x = L.blk.y = L.blk.z = 0x40000000;
-						L.occWord = 0;
-						L.hit = false;
-						state = ST_TILE;
+						const uint4* row = s_rays[warp][cur] + (idx & 31u);
+						const uint4 rInv = row[2 * 32];
+						if(rInv.w & WF_READY)
+						{
+							const uint4 rDir = row[0], rPos = row[1 * 32], rSide = row[3 * 32], rCell = row[4 * 32];
+							slot = idx;
+							L.dir = xyz_of(rDir);
+							L.inv = xyz_of(rInv);
+							L.pos = xyz_of(rPos);
+							L.st.lastVoxID = rDir.w;
+							L.st.lastVoxRefract = __uint_as_float(rPos.w);
+							L.st.tripped = (rInv.w & WF_TRIPPED) != 0u;
+							L.st.vox = make_uint4(0, 0, 0, 0);
+							L.m.pos.x = (int)rCell.x; L.m.pos.y = (int)rCell.y; L.m.pos.z = (int)rCell.z;
+							L.m.side = xyz_of(rSide);
+							L.m.delta = abs3(L.inv);
+							L.m.step.x = isgn(L.dir.x); L.m.step.y = isgn(L.dir.y); L.m.step.z = isgn(L.dir.z);
+							L.colorAdd = splat3(0.0f);
+							L.colorMult = 1.0f;
+							L.tLast = 0.0f;
+							L.ignoreFirst = true;
+							L.guard = 0;
+							L.blk.x = L.blk.y = L.blk.z = 0x40000000;
+							L.occWord = 0;
+							L.hit = false;
+							state = ST_TILE;
+						}
 					}
 				}
+				next += (uint32_t)nF;
+				if(nT + nV == 0)
+					continue; /* nobody was stepping: count again */
 			}
-			next += (uint32_t)nF;
-			continue;
+			else if(nT + nV == 0)
+				break; /* no range left (the cursor is past the pool) and every lane is idle */
 		}
 
-		if(nT >= nV)
+		/* the stepping phase with more lanes, until a quarter of them has left it */
+		const uint32_t mT2 = __ballot_sync(0xFFFFFFFFu, state == ST_TILE);
+		const uint32_t mV2 = __ballot_sync(0xFFFFFFFFu, state == ST_VOX);
+		const int cT = __popc(mT2), cV = __popc(mV2);
+		if(cT >= cV)
 		{
-			const int keep = (3 * nT + 3) >> 2;
+			const int keep = (3 * cT + 3) >> 2;
 #pragma unroll 1
 			for(int it = 0; it < K.budget; it++)
 			{
 				if(state == ST_TILE)
 					flat_tile_step(S, L, state);
-				waited++;
 				if(__popc(__ballot_sync(0xFFFFFFFFu, state == ST_TILE)) < keep)
 					break;
 			}
 		}
 		else
 		{
-			const int keep = (3 * nV + 3) >> 2;
+			const int keep = (3 * cV + 3) >> 2;
 #pragma unroll 1
 			for(int it = 0; it < K.budget; it++)
 			{
 				if(state == ST_VOX)
 					flat_vox_step(S, L, state);
-				waited++;
 				if(__popc(__ballot_sync(0xFFFFFFFFu, state == ST_VOX)) < keep)
 					break;
 			}
@@ -307,7 +347,7 @@ static DnbWaveHost g_wave;
 
 extern "C" size_t dnb_wave_slot_bytes(void) { return (size_t)WAVE_PLANES * sizeof(uint4); }
 
-/* ctx: WAVE_PLANES * P uint4; counters: 4 device words (work counter, two live-slot counters, spare) */
+/* ctx: WAVE_PLANES * P uint4, P a multiple of 256; counters: 4 device words (work counter, two live-slot counters, spare) */
 extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
                                              const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream)
 {
@@ -341,12 +381,15 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 	/* every slot idle, counters zero */
 	if((e = cudaMemsetAsync(ctx + (size_t)WV_DIFF * P, 0, (size_t)P * sizeof(uint4), stream)) != cudaSuccess)
 		return e;
+	if((e = cudaMemsetAsync(ctx + (size_t)WR_INV * P, 0, (size_t)P * sizeof(uint4), stream)) != cudaSuccess)
+		return e;
 	if((e = cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), stream)) != cudaSuccess)
 		return e;
 
 	const uint32_t totalItems = numCtas * 128u;
 	const uint32_t stepCtas = std::min<uint32_t>((uint32_t)g_wave.stepCtas, (P + 4u * WAVE_GRAB - 1u) / (4u * WAVE_GRAB));
 
+	static const bool trace = getenv("DN_B200_WAVE_TRACE") != nullptr;
 	uint32_t pass = 0;
 	for(;; pass++)
 	{
@@ -355,12 +398,14 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 			const uint32_t look = pass - WAVE_LAG;
 			if((e = cudaEventSynchronize(g_wave.ev[look & 7u])) != cudaSuccess)
 				return e;
+			if(trace)
+				fprintf(stderr, "wave pass %u: %u live slots of %u\n", look, g_wave.pinned[look & 7u], P);
 			if(g_wave.pinned[look & 7u] == 0u)
 				break; /* that pass left no live slot: every voxel of the dispatch is staged */
 		}
 		uint32_t* now = counters + 1 + (pass & 1u);
 		uint32_t* nxt = counters + 1 + ((pass + 1u) & 1u);
-		dn_wave_serve_kernel<<<P / 128u, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, totalItems, counters, *targets, ctx, P, now, nxt);
+		dn_wave_serve_kernel<<<P / WAVE_SERVE_THREADS, WAVE_SERVE_THREADS, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, totalItems, counters, *targets, ctx, P, now, nxt);
 		if((e = cudaMemcpyAsync(&g_wave.pinned[pass & 7u], now, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
 			return e;
 		if((e = cudaEventRecord(g_wave.ev[pass & 7u], stream)) != cudaSuccess)

@@ -1,18 +1,24 @@
 """aggregates `ncu --page source` counters of a report by named line regions of one source file.
-usage: python tools/ncu_regions.py report.ncu-rep file.cuh a-b:name [a-b:name ...]"""
+usage: python tools/ncu_regions.py [--kernel substr] report.ncu-rep file.cuh a-b:name [a-b:name ...]"""
 import csv
 import io
 import subprocess
 import sys
 
-rep, target = sys.argv[1], sys.argv[2]
+args = sys.argv[1:]
+kernel = None
+if "--kernel" in args:
+    i = args.index("--kernel")
+    kernel = args[i + 1]
+    del args[i:i + 2]
+rep, target = args[0], args[1]
 regions = []
-for spec in sys.argv[3:]:
+for spec in args[2:]:
     rng, name = spec.split(":")
     a, b = rng.split("-")
     regions.append((int(a), int(b), name))
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
-f, ix, agg = None, None, {}
+f, ix, agg, skip = None, None, {}, False
 
 
 def num(r, name):
@@ -28,10 +34,13 @@ for r in csv.reader(io.StringIO(txt)):
     if r[0] in ("File Path", "File Name"):
         f = r[1].split("/")[-1]
         continue
+    if r[0] == "Function Name":
+        skip = kernel is not None and kernel not in r[1]
+        continue
     if r[0] == "Line No":
         ix = {h: i for i, h in enumerate(r)}
         continue
-    if ix and r[0].isdigit() and len(r) > ix["Thread Instructions Executed"]:
+    if ix and not skip and r[0].isdigit() and len(r) > ix["Thread Instructions Executed"]:
         key = f
         if f == target:
             ln = int(r[0])
