@@ -319,6 +319,32 @@ static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const
 			}
 		}
 	slot->numVoxels = n;
+
+	/* bounding box of the surface voxels: T[y] byte z holds the x bits of row (y, z) */
+	unsigned xb = 0, yb = 0, zb = 0;
+	for(int y = 0; y < 8; y++)
+	{
+		if(T[y])
+			yb |= 1u << y;
+		for(int z = 0; z < 8; z++)
+		{
+			const unsigned row = (unsigned)((T[y] >> (8 * z)) & 0xFFu);
+			xb |= row;
+			if(row)
+				zb |= 1u << z;
+		}
+	}
+	if(n == 0)
+		slot->bbox = 0; /* nothing to hit; offsets of zero = no culling */
+	else
+	{
+		const unsigned mn[3] = {(unsigned)__builtin_ctz(xb), (unsigned)__builtin_ctz(yb), (unsigned)__builtin_ctz(zb)};
+		const unsigned mx[3] = {31u - (unsigned)__builtin_clz(xb), 31u - (unsigned)__builtin_clz(yb), 31u - (unsigned)__builtin_clz(zb)};
+		uint32_t bb = 0;
+		for(int a = 0; a < 3; a++)
+			bb |= ((7u - mx[a]) << (3 * a)) | (mn[a] << (9 + 3 * a));
+		slot->bbox = bb;
+	}
 	return n;
 }
 
@@ -1281,7 +1307,7 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 }
 
 /* pool size of the wavefront kernels: every voxel of the dispatch in flight at once when that fits, else the cap set with
- * DN_b200_set_wave_slots / $DN_B200_WAVE_SLOTS (default 1 Mi slots = 240 MiB; the passes then stream the dispatch through the pool) */
+ * DN_b200_set_wave_slots / $DN_B200_WAVE_SLOTS (default 4 Mi slots = 960 MiB; the passes then stream the dispatch through the pool) */
 static uint32_t g_waveSlots = 0;
 extern "C" void DN_b200_set_wave_slots(uint32_t slots)
 {
@@ -1292,7 +1318,7 @@ static uint32_t wave_pool_slots(uint32_t numCtas)
 	if(g_waveSlots == 0)
 	{
 		const char* env = getenv("DN_B200_WAVE_SLOTS");
-		DN_b200_set_wave_slots(env && atoll(env) >= 128 ? (uint32_t)std::min<long long>(atoll(env), 1ll << 26) : (1u << 20));
+		DN_b200_set_wave_slots(env && atoll(env) >= 128 ? (uint32_t)std::min<long long>(atoll(env), 1ll << 26) : (1u << 22));
 	}
 	const unsigned long long items = ((unsigned long long)numCtas * 128ull + 255ull) & ~255ull; /* the serve kernel's CTAs hold 256 slots */
 	return (uint32_t)std::min<unsigned long long>(items, g_waveSlots);

@@ -45,7 +45,8 @@ typedef struct DNB_ALIGN(128) DnbSlot
 	uint32_t mapIndex;    /* owner tile */
 	uint16_t prefix[16];  /* records before mask word i */
 	int32_t  pos[3];      /* owner tile position */
-	uint32_t pad;
+	uint32_t bbox;        /* bounding box of the surface voxels, ready to use as cell offsets (trace.cuh "exact chunk cull"):
+	                         bits [3a, 3a+3) = 7 - max on axis a (rays stepping up), bits [9+3a, 12+3a) = min on axis a (rays stepping down) */
 } DnbSlot;
 
 /* material as the kernels read it; 32 bytes like DNmaterial, same field order (voxel.h:82-94) */

@@ -65,6 +65,7 @@ struct FlatLane
 	float    ctLast;
 	const DnbSlot* slot;
 	uint32_t wordIdx, word, cguard, mapIndex;
+	uint32_t cbias, coffp;   /* exact chunk cull (trace.cuh cull_offsets): cp is shifted by the offsets in coffp */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -146,6 +147,10 @@ DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 		L.cguard = 0;
 		L.wordIdx = 0xFFFFFFFFu;
 		L.word = 0;
+		L.cbias = 0;
+		L.coffp = 0;
+		if(L.st.lastVoxID == 255u)
+			L.coffp = cull_offsets(__ldg(&L.slot->bbox), m.step, L.cp, L.cbias);
 		state = ST_VOX;
 		return;
 	}
@@ -171,7 +176,7 @@ DNB_FN void flat_vox_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 		return;
 	}
 
-	const uint32_t local = (uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z);
+	const uint32_t local = ((uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z)) - L.cbias;
 	if((local >> 5) != L.wordIdx)
 	{
 		L.wordIdx = local >> 5;
@@ -199,6 +204,8 @@ DNB_FN void flat_vox_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 		}
 		else if(L.st.lastVoxID != thisVoxID)
 		{
+			if(L.coffp)
+				cull_undo(L.coffp, L.cp, L.cbias);
 			const float cm = L.colorMult * material.opacity;
 			L.colorAdd = L.colorAdd + (vox_albedo(rec) * cm) * ld3(S.sunStrength);
 			L.colorMult = L.colorMult * (1.0f - material.opacity);

@@ -141,6 +141,34 @@ DNB_FN bool in_chunk_bounds(i3 p)
 	return ((uint32_t)(p.x | p.y | p.z)) < 8u;
 }
 
+/* Exact chunk cull.  The voxel-level DDA only ever moves each coordinate in its ray's direction, so once the cell is past the
+ * bounding box of the chunk's surface voxels on an axis -- beyond its maximum going up, below its minimum going down -- no voxel
+ * of the chunk can be hit any more, and nothing of the voxel-level state is read after the chunk has been left without a hit.
+ * Instead of testing that, the cell is stored SHIFTED per axis (by 7 - max going up, by -min going down; DnbSlot.bbox holds both
+ * ready-made) so that the ordinary chunk-bounds test of the loop fires exactly there; the voxel index subtracts the shift again.
+ * A ray that enters the chunk already past the box never runs the loop at all.  Only empty voxels are skipped, and an empty
+ * voxel matters only while the ray is inside a transparent block (lastVoxID != 255: the state is reset there, and the draw pass
+ * refracts), so the shift is used only while lastVoxID == 255 and is taken back the moment a transparent voxel is met.
+ * Returns the packed shift: bits 0-3 / 4-7 / 8-11 = x / y / z offsets as 4-bit two's complement. */
+DNB_FN uint32_t cull_offsets(uint32_t bbox, i3 step, i3& pos, uint32_t& bias)
+{
+	const int ox = step.x > 0 ? (int)(bbox & 7u) : -(int)((bbox >> 9) & 7u);
+	const int oy = step.y > 0 ? (int)((bbox >> 3) & 7u) : -(int)((bbox >> 12) & 7u);
+	const int oz = step.z > 0 ? (int)((bbox >> 6) & 7u) : -(int)((bbox >> 15) & 7u);
+	pos.x += ox; pos.y += oy; pos.z += oz;
+	bias = (uint32_t)(ox + 8 * oy + 64 * oz);
+	return ((uint32_t)ox & 15u) | (((uint32_t)oy & 15u) << 4) | (((uint32_t)oz & 15u) << 8);
+}
+
+DNB_FN void cull_undo(uint32_t& offp, i3& pos, uint32_t& bias)
+{
+	pos.x -= ((int)(offp << 28)) >> 28;
+	pos.y -= ((int)(offp << 24)) >> 28;
+	pos.z -= ((int)(offp << 20)) >> 28;
+	offp = 0;
+	bias = 0;
+}
+
 #define DNB_COUNT(field) do { if(COUNT) lc.field++; } while(0)
 
 /* step_map + step_chunk.  REFRACT: enableRefraction (true in draw, false in lighting, DR:65 / LI:209); only then is
@@ -244,6 +272,9 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 
 			uint32_t cguard = 0;
 			uint32_t wordIdx = 0xFFFFFFFFu, word = 0;
+			uint32_t bias = 0, offp = 0; /* exact chunk cull (see cull_offsets): c.pos is shifted by the offsets in offp */
+			if(!COUNT && st.lastVoxID == 255u)
+				offp = cull_offsets(__ldg(&slot->bbox), c.step, c.pos, bias);
 			while(in_chunk_bounds(c.pos))
 			{
 				if(++cguard > DNB_MAX_CHUNK_STEPS)
@@ -253,7 +284,7 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 				}
 				DNB_COUNT(voxelSteps);
 
-				const uint32_t local = (uint32_t)c.pos.x + 8u * ((uint32_t)c.pos.y + 8u * (uint32_t)c.pos.z);
+				const uint32_t local = ((uint32_t)c.pos.x + 8u * ((uint32_t)c.pos.y + 8u * (uint32_t)c.pos.z)) - bias;
 				if((local >> 5) != wordIdx)
 				{
 					wordIdx = local >> 5;
@@ -284,6 +315,8 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 					}
 					else if(st.lastVoxID != thisVoxID)
 					{
+						if(offp)
+							cull_undo(offp, c.pos, bias); /* inside a transparent block every empty voxel counts */
 						/* SH:365-366, maxDepth < 0 */
 						const float cm = colorMult * material.opacity;
 						colorAdd = colorAdd + (vox_albedo(rec) * cm) * ld3(S.sunStrength);

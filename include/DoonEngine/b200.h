@@ -55,7 +55,7 @@ bool DN_b200_read_hits(GLuint fb, DNb200hit* dst, size_t count);
  * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat" | "wave" | "auto". ---- */
 void DN_b200_set_light_kernel(int which);
 int  DN_b200_get_light_kernel(void);
-/* context-pool size of the wavefront kernels (rounded to a multiple of 128; 0 = default / $DN_B200_WAVE_SLOTS = 1 Mi slots of 240
+/* context-pool size of the wavefront kernels (rounded to a multiple of 128; 0 = default / $DN_B200_WAVE_SLOTS = 4 Mi slots of 240
  * bytes).  A dispatch with more voxels than slots is streamed through the pool; results do not depend on the size. */
 void DN_b200_set_wave_slots(uint32_t slots);
 /* scheduling knobs of the persistent kernel (see csrc/light_flat.cuh); results do not depend on them.  0 = defaults / environment */

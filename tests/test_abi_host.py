@@ -186,6 +186,12 @@ def test_host_packing_matches_oracle(oracle_mod):
                 assert int(slot["prefix"][w]) == run
                 run += bin(int(slot["mask"][w])).count("1")
             assert np.array_equal(grec, np.asarray(recs, dtype=np.uint32)), "%s: records of tile %d" % (what, tile)
+            # bounding box of the surface voxels, stored as ready-made cell offsets (csrc/trace.cuh cull_offsets)
+            bits = np.unpackbits(np.asarray(slot["mask"], dtype="<u4").view(np.uint8), bitorder="little").reshape(8, 8, 8)  # [z][y][x]
+            zs, ys, xs = np.nonzero(bits)
+            bb = int(slot["bbox"])
+            for a, c in enumerate((xs, ys, zs)):
+                assert (bb >> (3 * a)) & 7 == 7 - int(c.max()) and (bb >> (9 + 3 * a)) & 7 == int(c.min()), "%s: bbox of tile %d axis %d" % (what, tile, a)
         return len(st)
 
     # bundled demo map
