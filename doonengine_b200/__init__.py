@@ -110,6 +110,7 @@ MATERIAL_DT = np.dtype([("pad", "<f4", 2), ("emissive", "<u4"), ("opacity", "<f4
                         ("specular", "<f4"), ("reflectType", "<u4"), ("shininess", "<u4")])
 SLOT_DT = np.dtype([("mask", "<u4", 16), ("voxelBase", "<u4"), ("numVoxels", "<u4"), ("numSamples", "<u4"),
                     ("mapIndex", "<u4"), ("prefix", "<u2", 16), ("pos", "<i4", 3), ("bbox", "<u4")])
+VOXEL_DT = np.dtype([("material", "u1"), ("normal", "<f4", 3), ("albedo", "u1", 3)], align=True)  # DNvoxel (voxel.h:44-52), 20 bytes
 HIT_DT = np.dtype([("status", "<i4"), ("mapIndex", "<u4"), ("localIndex", "<u4"), ("recordIndex", "<u4")])
 assert HOST_CHUNK_DT.itemsize == 4120 and HOST_HANDLE_DT.itemsize == 8 and MATERIAL_DT.itemsize == 32 and SLOT_DT.itemsize == 128
 
@@ -185,6 +186,7 @@ _PROTOTYPES = {
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
     "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
+    "DN_b200_step_map_batch": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "DN_b200_set_wave_slots": (None, [C.c_uint32]),
     "DN_b200_set_chunks": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
     "DN_b200_save_lighting": (C.c_bool, [C.POINTER(DNvolume), C.c_char_p]),
@@ -385,6 +387,27 @@ class Engine:
         v = np.ascontiguousarray(voxels, dtype=np.uint32)
         assert p.ndim == 2 and p.shape[1] == 3 and v.shape == (p.shape[0], 2)
         return int(self.L.DN_b200_set_voxels(self.vol, p.shape[0], p.ctypes.data, v.ctypes.data))
+
+    def step_map_batch(self, dirs, origins, max_steps):
+        """DN_step_map for many rays at once on the device map (DN_b200_step_map_batch).  dirs / origins: float32 [n,3] (origins in
+        chunk units).  Returns dict(hit uint8 [n], pos int32 [n,3], normal int32 [n,3], voxel structured [n] (DNvoxel fields))."""
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        assert d.ndim == 2 and d.shape[1] == 3 and o.shape == d.shape
+        n = d.shape[0]
+        hit = np.zeros(n, np.uint8)
+        pos = np.zeros((n, 3), np.int32)
+        normal = np.zeros((n, 3), np.int32)
+        voxel = np.zeros(n, VOXEL_DT)
+        hits = self.L.DN_b200_step_map_batch(self.vol, n, d.ctypes.data, o.ctypes.data, int(max_steps), pos.ctypes.data, voxel.ctypes.data, normal.ctypes.data, hit.ctypes.data)
+        assert hits == int(hit.sum())
+        return dict(hit=hit, pos=pos, normal=normal, voxel=voxel)
+
+    def step_map(self, direction, origin, max_steps):
+        """one DN_step_map call (CPU map, voxel.c:1195-1272): (hit, pos, normal, voxel fields) like one row of step_map_batch."""
+        hp, hn, hv = DNivec3(), DNivec3(), DNvoxel()
+        ok = bool(self.L.DN_step_map(self.vol, DNvec3(*[float(x) for x in direction]), DNvec3(*[float(x) for x in origin]), int(max_steps), C.byref(hp), C.byref(hv), C.byref(hn)))
+        return ok, (hp.x, hp.y, hp.z), (hn.x, hn.y, hn.z), hv
 
     def pack_chunk(self, map_pos):
         """(slot header as SLOT_DT scalar, records uint32 [n,4]) of the chunk at map_pos as the next writing sync would upload it;

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdoon_b200.so")
 SCENES_LIB = os.path.join(HERE, "libdoon_scenes.so")  # native generators of the large synthetic maps (bench / tests only)
 
-SOURCES = ["draw.cu", "light.cu", "compact.cu", "upload.cu", "peer.cu", "engine.cpp", "volume_host.cpp"]
+SOURCES = ["draw.cu", "light.cu", "compact.cu", "upload.cu", "peer.cu", "pick.cu", "engine.cpp", "volume_host.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh")))  # every header: a stale library is worse than a slow build
 PUBLIC_HEADERS = ["DoonEngine/voxel.h", "DoonEngine/b200.h", "DoonEngine/globals.h", "DoonEngine/mathtypes.h"]
 

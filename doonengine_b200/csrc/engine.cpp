@@ -134,7 +134,7 @@ void device_destroy(VolumeImpl* v)
 	}
 	device_free(v->tileSlot); device_free(v->occ64); device_free(v->visible); device_free(v->propagate); device_free(v->forced);
 	device_free(v->slots); device_free(v->records); device_free(v->materials); device_free(v->requests); device_free(v->staging);
-	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->waveCtx); device_free(v->blob); device_free(v->litCounter);
+	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->waveCtx); device_free(v->pickRays); device_free(v->pickHits); device_free(v->blob); device_free(v->litCounter);
 	device_free(v->mailbox); device_free(v->barrierStatus);
 	v->peerAttached = false;
 	for(int slot = 0; slot < 2; slot++)
@@ -1826,6 +1826,95 @@ extern "C" bool DN_b200_peer_barrier_status(DNvolume* vol, uint64_t* epochs, uin
 
 /* ------------------------------------------------------------------------------------------------ */
 /* lit-state checkpoint: the reference saves only the map (voxel.c:595-654); after a load every chunk */
+/* ------------------------------------------------------------------------------------------------ */
+/* batched picking: DN_step_map (voxel.c:1195-1272) for `count` rays on the device map (pick.cu)      */
+
+extern "C" size_t DN_b200_step_map_batch(DNvolume* vol, size_t count, const DNvec3* rayDirs, const DNvec3* rayPositions, int maxSteps, DNivec3* hitPositions, DNvoxel* hitVoxels,
+                                         DNivec3* hitNormals, uint8_t* hitFlags)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(count == 0 || !device_ready(v, "DN_b200_step_map_batch"))
+		return 0;
+	if(count > 0x7FFFFFFFu)
+	{
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_step_map_batch: at most 2^31 - 1 rays per call");
+		return 0;
+	}
+	/* DN_step_map sees every edit at once (it reads the CPU map); so must this: pending edits are uploaded first.  A replica of a
+	 * peer-attached volume cannot do that on its own (the upload is fenced against the other replicas): its caller syncs. */
+	if(!v->touched.empty() && !v->peerAttached)
+		sync_write(v);
+
+	cudaStream_t s = ctx().stream();
+	if(!device_reserve(v->pickRays, count * 6, false, false, "picking rays") || !device_reserve(v->pickHits, count, false, false, "picking results"))
+		return 0;
+	bool ok = cuda_ok(cudaMemcpyAsync(v->pickRays.ptr, rayDirs, count * sizeof(DNvec3), cudaMemcpyHostToDevice, s), "picking directions");
+	ok = ok && cuda_ok(cudaMemcpyAsync(v->pickRays.ptr + count * 3, rayPositions, count * sizeof(DNvec3), cudaMemcpyHostToDevice, s), "picking origins");
+	DnbScene scene;
+	fill_scene(v, &scene);
+	ok = ok && cuda_ok(dnb_launch_pick(&scene, v->pickRays.ptr, v->pickRays.ptr + count * 3, (uint32_t)count, maxSteps, v->pickHits.ptr, s), "picking kernel");
+	std::vector<int4> res(count);
+	ok = ok && cuda_ok(cudaMemcpyAsync(res.data(), v->pickHits.ptr, count * sizeof(int4), cudaMemcpyDeviceToHost, s), "picking read-back");
+	ok = ok && cuda_ok(cudaStreamSynchronize(s), "picking");
+	if(!ok)
+		return 0;
+
+	size_t hits = 0;
+	for(size_t i = 0; i < count; i++)
+	{
+		bool hit = false;
+		DNivec3 pos = {0, 0, 0}, normal = {-1000, -1000, -1000};
+		if(maxSteps > 0)
+		{
+			/* the cell the ray starts in, from the CPU map: the only voxel a ray can find that the device (surface voxels only) may not hold */
+			const DNivec3 start = {(int)floor(rayPositions[i].x * DN_CHUNK_SIZE), (int)floor(rayPositions[i].y * DN_CHUNK_SIZE), (int)floor(rayPositions[i].z * DN_CHUNK_SIZE)};
+			if(start.x >= 0 && start.y >= 0 && start.z >= 0)
+			{
+				DNivec3 mapPos, chunkPos;
+				DN_separate_position(start, &mapPos, &chunkPos);
+				if(DN_in_map_bounds(vol, mapPos) && DN_does_chunk_exist(vol, mapPos) && DN_does_voxel_exist(vol, mapPos, chunkPos))
+				{
+					hit = true;
+					pos = start;
+				}
+			}
+			if(!hit)
+			{
+				const int4 r = res[i];
+				const uint32_t code = (uint32_t)r.w;
+				const uint32_t axis = (code >> 1) & 3u;
+				if(axis < 3u)
+				{
+					normal.x = normal.y = normal.z = 0;
+					(&normal.x)[axis] = (code & 16u) ? 0 : ((code & 8u) ? -1 : 1); /* -rayStep of the last step (voxel.c:1268-1269) */
+				}
+				if(code & 1u)
+				{
+					hit = true;
+					pos.x = r.x; pos.y = r.y; pos.z = r.z;
+				}
+			}
+		}
+		if(hitNormals)
+			hitNormals[i] = normal;
+		if(hitFlags)
+			hitFlags[i] = hit ? 1 : 0;
+		if(hit)
+		{
+			hits++;
+			if(hitPositions)
+				hitPositions[i] = pos;
+			if(hitVoxels)
+			{
+				DNivec3 mapPos, chunkPos;
+				DN_separate_position(pos, &mapPos, &chunkPos);
+				hitVoxels[i] = DN_get_voxel(vol, mapPos, chunkPos);
+			}
+		}
+	}
+	return hits;
+}
+
 /* re-accumulates its lighting from zero samples.  These two calls carry the accumulated lighting across a save / load.  */
 
 namespace

@@ -86,6 +86,8 @@ struct VolumeImpl
 	DeviceArray<uint32_t>           staging;   /* 96 words per request */
 	DeviceArray<uint32_t>           blockCounts, blockOffsets, scalars;
 	DeviceArray<uint32_t>           forcedList;
+	DeviceArray<float>              pickRays;  /* DN_b200_step_map_batch: 3 floats of direction, 3 of origin per ray */
+	DeviceArray<int4>               pickHits;
 	DeviceArray<uint4>              waveCtx;   /* context pool of the wavefront lighting kernels (light_wave.cuh), allocated on first use */
 	DeviceArray<unsigned long long> litCounter; /* voxel lighting updates committed since creation */
 	DeviceArray<unsigned char>      blob;      /* device side of the upload batch */

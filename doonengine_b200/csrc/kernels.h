@@ -38,6 +38,9 @@ cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* request
 cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
                               unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream);
 
+/* pick.cu: `count` DN_step_map rays (voxel.c:1195-1272) on the device map; out[i] = {cell, code} (see dn_pick_kernel) */
+cudaError_t dnb_launch_pick(const DnbScene* scene, const float* dirs, const float* origins, uint32_t count, int maxSteps, int4* out, cudaStream_t stream);
+
 /* peer.cu: device-side barrier over the replicas' mailboxes, and visible |= every peer's visible */
 cudaError_t dnb_launch_peer_barrier(const DnbPeerTable* peers, uint32_t epoch, uint32_t* status, cudaStream_t stream);
 cudaError_t dnb_launch_peer_or_visible(const DnbPeerTable* peers, uint32_t* visible, uint32_t words, cudaStream_t stream);

@@ -339,40 +339,62 @@ __global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_
 	}
 }
 
-/* phase 2: one warp per request */
+/* phase 2: one warp per request, persistent grid-stride warps.  The lit-voxel count (the metric's numerator) is summed per warp and
+ * per CTA and added with ONE atomic per CTA: with one atomic per request the 10^7 same-address atomics of a full-size dispatch
+ * WERE the kernel (11.4 ms for 10.9 M requests on B200, 1.2 TB/s; the streaming itself needs a quarter of that). */
 __global__ void __launch_bounds__(256) dn_commit_kernel(const uint32_t* __restrict__ tileSlot, DnbSlot* __restrict__ slots, uint4* __restrict__ records, uint32_t* __restrict__ visible,
                                                         const uint32_t* __restrict__ requests, uint32_t numRequests, const uint32_t* __restrict__ staging,
                                                         unsigned long long* __restrict__ litCounter)
 {
-	const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-	if(r >= numRequests)
-		return;
-	const uint32_t request = __ldg(requests + r);
-	const uint32_t mapIndex = request >> 4, group = request & 15u;
-	const uint32_t slotId = __ldg(tileSlot + mapIndex) - 1u;
-	if(slotId == 0xFFFFFFFFu)
-		return;
+	__shared__ uint32_t s_lit[8];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t lit = 0;
+	for(uint32_t r = blockIdx.x * 8 + warp; r < numRequests; r += gridDim.x * 8)
+	{
+		const uint32_t request = __ldg(requests + r);
+		const uint32_t mapIndex = request >> 4, group = request & 15u;
+		const uint32_t slotId = __ldg(tileSlot + mapIndex) - 1u;
+		if(slotId == 0xFFFFFFFFu)
+			continue;
 
-	DnbSlot* slot = slots + slotId;
-	const uint32_t numVoxels = slot->numVoxels, base = slot->voxelBase;
-	const uint32_t voxNum = lane + group * 32u;
-	const uint32_t live = __ballot_sync(0xFFFFFFFFu, voxNum < numVoxels);
-	if(voxNum < numVoxels)
-	{
-		const uint32_t* in = staging + (size_t)r * 96u;
-		uint4 rec;
-		rec.x = records[base + voxNum].x;
-		rec.y = __ldg(in + lane);
-		rec.z = __ldg(in + 32 + lane);
-		rec.w = __ldg(in + 64 + lane);
-		records[base + voxNum] = rec;
+		DnbSlot* slot = slots + slotId;
+		const uint32_t numVoxels = slot->numVoxels, base = slot->voxelBase;
+		const uint32_t voxNum = lane + group * 32u;
+		if(voxNum < numVoxels)
+		{
+			const uint32_t* in = staging + (size_t)r * 96u;
+			uint4 rec;
+			rec.x = records[base + voxNum].x;
+			rec.y = __ldg(in + lane);
+			rec.z = __ldg(in + 32 + lane);
+			rec.w = __ldg(in + 64 + lane);
+			records[base + voxNum] = rec;
+		}
+		if(group * 32u < numVoxels)
+		{
+			if(lane == 0)
+			{
+				/* LI:281; the groups of a chunk all clear the same bit: whoever still sees it set clears it */
+				const uint32_t bit = 1u << (mapIndex & 31u);
+				if(*reinterpret_cast<volatile uint32_t*>(visible + (mapIndex >> 5)) & bit)
+					atomicAnd(visible + (mapIndex >> 5), ~bit);
+				if(group == 0)
+					slot->numSamples = slot->numSamples + 1u;
+			}
+			const uint32_t left = numVoxels - group * 32u;
+			lit += left < 32u ? left : 32u;
+		}
 	}
-	if(lane == 0 && group * 32u < numVoxels)
+	if(lane == 0)
+		s_lit[warp] = lit;
+	__syncthreads();
+	if(threadIdx.x == 0)
 	{
-		atomicAnd(visible + (mapIndex >> 5), ~(1u << (mapIndex & 31u)));
-		if(group == 0)
-			slot->numSamples = slot->numSamples + 1u;
-		atomicAdd(litCounter, (unsigned long long)__popc(live)); /* the metric's numerator: voxel lighting updates */
+		unsigned long long total = 0;
+		for(int w = 0; w < 8; w++)
+			total += s_lit[w];
+		if(total)
+			atomicAdd(litCounter, total); /* the metric's numerator: voxel lighting updates */
 	}
 }
 
@@ -465,7 +487,17 @@ extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, 
 {
 	if(numRequests > 0)
 	{
-		dn_commit_kernel<<<(numRequests + 7) / 8, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging, litCounter);
+		/* persistent: 8 CTAs of 8 warps per SM at most (the kernel streams; its warps only wait on memory) */
+		static int maxCtas = 0;
+		if(maxCtas == 0)
+		{
+			int dev = 0, sms = 148;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			maxCtas = sms * 8;
+		}
+		const uint32_t ctas = std::min<uint32_t>((numRequests + 7) / 8, (uint32_t)maxCtas);
+		dn_commit_kernel<<<ctas, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging, litCounter);
 		cudaError_t e = cudaGetLastError();
 		if(e != cudaSuccess)
 			return e;

@@ -11,7 +11,7 @@
  *
  * Why: in dn_light_flat_kernel (one context per lane, in registers) ncu attributes ~40 % of all issue slots to ray set-up and
  * shading executed with 2-4 active lanes, and the stepping phases run with 7-9 lanes because half the warp is waiting for that
- * service (profiles/r2_wave.md).  Moving the contexts to memory costs ~0.3 KB of traffic per ray segment and buys full warps
+ * service (profiles/r1_v3_wave.md).  Moving the contexts to memory costs ~0.3 KB of traffic per ray segment and buys full warps
  * for shading and twice the lanes for stepping.  Nothing about a voxel's own sequence of operations changes -- the same
  * functions run in the same order on the same values -- so the staged words are bit-identical to both other kernels
  * (tests/test_parity_gpu.py runs every lighting test against all three).

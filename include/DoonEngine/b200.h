@@ -120,6 +120,14 @@ size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions,
  * are skipped; returns the number of chunks present afterwards among those given */
 size_t DN_b200_set_chunks(DNvolume* vol, size_t count, const DNivec3* mapPositions, const DNcompressedVoxel* voxels);
 
+/* ---- batched picking: DN_step_map (voxel.c:1195-1272) for `count` rays in one call, walked on the DEVICE map (csrc/pick.cu: the
+ * reference's single-axis voxel DDA over the occupancy bit-grid and the chunks' surface masks).  Per ray the outputs are exactly
+ * what DN_step_map would return: hitFlags[i] = its return value; hitNormals[i] is always written (-1000 if no step was taken);
+ * hitPositions[i] / hitVoxels[i] only on a hit.  Any output array may be NULL.  Pending edits are uploaded first (a writing sync),
+ * except on a peer-attached replica, whose caller must DN_sync_gpu(DN_WRITE) itself.  Returns the number of hits. ---- */
+size_t DN_b200_step_map_batch(DNvolume* vol, size_t count, const DNvec3* rayDirs, const DNvec3* rayPositions, int maxSteps, DNivec3* hitPositions, DNvoxel* hitVoxels,
+                              DNivec3* hitNormals, uint8_t* hitFlags);
+
 /* ---- lit-state checkpoint: DN_save_volume / DN_load_volume persist only the map (voxel.c:520-654), so upstream every chunk
  * re-accumulates its lighting from zero samples after a load.  These carry the accumulated lighting (the three lit words of every
  * record + each chunk's sample count) across: save any time; load after DN_load_volume + a writing DN_sync_gpu.  Chunks whose

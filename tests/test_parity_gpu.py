@@ -520,3 +520,63 @@ def test_kernels_agree_on_sparse_map_with_streamed_pool(dn, light_kernel):
         L.DN_b200_set_wave_slots(0)
         L.DN_b200_set_light_kernel(2)
         e.close()
+
+
+def test_batched_picking_equals_step_map(dn, light_kernel):
+    """DN_b200_step_map_batch (device map, csrc/pick.cu) returns exactly what DN_step_map (CPU map, reference voxel.c:1195-1272) returns
+    ray by ray: hit flag, hit cell, entry-face normal, voxel contents -- rays from outside and inside the map, starting inside solid
+    (culled interior voxels included), axis-parallel and zero direction components, negative coordinates, tiny step budgets, and
+    after edits that have not been synced yet."""
+    if light_kernel != "warp":
+        pytest.skip("no lighting involved")
+    from doonengine_b200 import scenes
+    rng = np.random.default_rng(11)
+
+    def rays(n, tiles):
+        t = np.array(tiles, np.float32)
+        o = (rng.random((n, 3), dtype=np.float32) * (t + 2.0) - 1.0).astype(np.float32)   # chunk units, some outside the map
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        k = n // 10
+        d[:k] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice(np.array([-1.0, 1.0], np.float32), (k, 1))   # axis-parallel
+        d[k:2 * k, rng.integers(0, 3)] = 0.0                                                                                    # one zero component
+        o[2 * k:3 * k] = np.floor(o[2 * k:3 * k] * 8.0) / 8.0                                                                   # starts on cell faces
+        return d, o
+
+    def check(e, d, o, steps, what):
+        got = e.step_map_batch(d, o, steps)
+        nhit = 0
+        for i in range(d.shape[0]):
+            ok, pos, nrm, vox = e.step_map(d[i], o[i], steps)
+            assert bool(got["hit"][i]) == ok, "%s ray %d: hit flag" % (what, i)
+            assert tuple(int(x) for x in got["normal"][i]) == nrm, "%s ray %d: normal %s vs %s" % (what, i, got["normal"][i], nrm)
+            if ok:
+                nhit += 1
+                assert tuple(int(x) for x in got["pos"][i]) == pos, "%s ray %d: cell %s vs %s" % (what, i, got["pos"][i], pos)
+                g = got["voxel"][i]
+                assert int(g["material"]) == vox.material and tuple(int(x) for x in g["albedo"]) == (vox.albedo.r, vox.albedo.g, vox.albedo.b)
+                assert tuple(float(x) for x in g["normal"]) == (vox.normal.x, vox.normal.y, vox.normal.z)
+        return nhit
+
+    # bundled demo map
+    e = dn.Engine(voxvol=DEMO, min_chunks=256)
+    e.sync(1, 1)
+    d, o = rays(3000, e.map_size)
+    assert check(e, d, o, 400, "demo") > 500
+    assert check(e, d[:300], o[:300], 3, "demo, 3 steps") >= 0
+    assert check(e, d[:50], o[:50], 0, "demo, no steps") == 0
+    e.close()
+
+    # terrain: solid ground (rays starting inside culled interior voxels), then unsynced edits
+    tiles = (8, 8, 8)
+    e = dn.Engine(map_size=tiles, min_chunks=600)
+    scenes.build(e, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+    e.sync(1, 1)
+    d, o = rays(3000, tiles)
+    o[:, 1] *= 0.6  # more origins below the surface
+    assert check(e, d, o, 300, "terrain") > 1000
+    pos = rng.integers(0, 64, (400, 3)).astype(np.int32)
+    vox = np.stack([np.where(rng.random(400) < 0.5, 0xFFFFFFFF, 0x007FFF7F), np.full(400, 0x80402000)], axis=1).astype(np.uint32)
+    e.set_voxels(pos, vox)  # NOT synced: the batch call uploads pending edits itself
+    assert check(e, d, o, 300, "terrain after edits") > 1000
+    e.close()
