@@ -1430,6 +1430,15 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
 	int timingSlot = -1;
 	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
+	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself; the other two stage locally and
+	 * their rows are pushed to the peers afterwards (light.cu dn_push_staging_kernel) */
+	DnbStagingTargets allPeers = targets;
+	const bool pushAfter = v->peerAttached && kernel != 0 && targets.count > 1;
+	if(pushAfter)
+	{
+		targets.count = 1;
+		targets.dst[0] = allPeers.dst[v->peers.rank];
+	}
 	if(kernel == 2)
 	{
 		const uint32_t P = wave_pool_slots(numCtas);
@@ -1438,6 +1447,8 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	}
 	else
 		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
+	if(pushAfter)
+		ok = ok && cuda_ok(dnb_launch_push_staging(&allPeers, v->peers.rank, firstCta, ctaStride, numCtas, limit, s), "staging push");
 	if(timingSlot >= 0)
 		cudaEventRecord(v->tuner.end[timingSlot], s);
 	v->tuner.launches[kernel]++;

@@ -34,6 +34,9 @@ cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, ui
 size_t      dnb_wave_slot_bytes(void);
 cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
                                   const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream);
+/* copies the staged rows of the CTAs firstCta, firstCta + ctaStride, ... from replica `self`'s staging array (peers->dst[self]) into every
+ * other replica's (coalesced 16-byte stores over NVLink); used after the persistent / wavefront kernels, which stage locally */
+cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests, cudaStream_t stream);
 /* peers: NULL, or the table whose propagate bitmaps (all replicas') are ORed into visible instead of only the local one */
 cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
                               unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream);

@@ -482,6 +482,41 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 	return cudaGetLastError();
 }
 
+/* Multi-GPU, persistent / wavefront kernels: their lanes finish voxels one at a time, so storing each voxel's three words straight
+ * into every replica means 4-byte stores scattered over NVLink (one packet each; measured: the wavefront kernels 45 % slower at 4
+ * replicas than at 1).  Those kernels therefore stage into their own replica only, and this kernel then pushes the rows of the CTAs
+ * the replica owns (4 requests = 1536 contiguous bytes each) to the other replicas with coalesced 16-byte stores.  (The
+ * warp-per-request kernel keeps its fused 128-byte row stores: its dispatches are latency-critical.) */
+__global__ void __launch_bounds__(128) dn_push_staging_kernel(const uint4* __restrict__ own, DnbStagingTargets T, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests)
+{
+	for(uint32_t k = blockIdx.x; k < numCtas; k += gridDim.x)
+	{
+		const uint32_t cta = firstCta + k * ctaStride;
+		const uint32_t firstRequest = cta * 4u;
+		if(firstRequest >= numRequests)
+			break;
+		const uint32_t rows = numRequests - firstRequest < 4u ? numRequests - firstRequest : 4u;
+		if(threadIdx.x < rows * 24u) /* 96 words = 24 uint4 per request */
+		{
+			const size_t at = (size_t)cta * 96u + threadIdx.x;
+			const uint4 v = own[at];
+#pragma unroll
+			for(uint32_t p = 0; p < DNB_MAX_PEERS; p++)
+				if(p < T.count && p != self)
+					reinterpret_cast<uint4*>(T.dst[p])[at] = v;
+		}
+	}
+}
+
+extern "C" cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests, cudaStream_t stream)
+{
+	if(numCtas == 0 || numRequests == 0 || peers->count < 2)
+		return cudaSuccess;
+	const uint32_t grid = numCtas < 148u * 16u ? numCtas : 148u * 16u;
+	dn_push_staging_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(peers->dst[self]), *peers, self, firstCta, ctaStride, numCtas, numRequests);
+	return cudaGetLastError();
+}
+
 extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
                                          unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream)
 {

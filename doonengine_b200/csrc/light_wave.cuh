@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128, WAVE_MIN_BLOCKS) dn_wave_step_kernel(DnbS
 		const int cT = __popc(mT2), cV = __popc(mV2);
 		if(cT >= cV)
 		{
-			const int keep = (3 * cT + 3) >> 2;
+			const int keep = (K.endLanes * cT + 7) >> 3;
 #pragma unroll 1
 			for(int it = 0; it < K.budget; it++)
 			{
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(128, WAVE_MIN_BLOCKS) dn_wave_step_kernel(DnbS
 		}
 		else
 		{
-			const int keep = (3 * cV + 3) >> 2;
+			const int keep = (K.endLanes * cV + 7) >> 3;
 #pragma unroll 1
 			for(int it = 0; it < K.budget; it++)
 			{
@@ -374,8 +374,8 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 	{
 		auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v && atoi(v) > 0 ? atoi(v) : dflt; };
 		tuning.budget = knob("DN_B200_WAVE_BUDGET", 24);
-		tuning.endLanes = knob("DN_B200_WAVE_FETCH", 8);
-		tuning.patience = knob("DN_B200_WAVE_PATIENCE", 4);
+		tuning.endLanes = knob("DN_B200_WAVE_KEEP", 4); /* a stepping burst ends once fewer than keep/8 of its lanes are still in the phase */
+		tuning.patience = 0;
 	}
 
 	/* every slot idle, counters zero */
