@@ -1417,7 +1417,12 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 			firstCta = (uint32_t)(first / 4);
 			numCtas = (uint32_t)((count + 3) / 4);
 		}
-		if(!device_reserve(v->staging, paddedTotal * 96, false, false, "lighting staging"))
+		/* grown with half as much again in reserve: the request count creeps up frame by frame while a map is being edited, and
+		 * every reallocation synchronises the device (config 4: a cudaMalloc + cudaFree per frame showed up as 6 ms of "lighting") */
+		size_t want = paddedTotal * 96;
+		if(want > v->staging.cap)
+			want = std::max(want, v->staging.cap + v->staging.cap / 2);
+		if(!device_reserve(v->staging, want, false, false, "lighting staging"))
 			return false;
 		targets.count = 1;
 		targets.dst[0] = v->staging.ptr;
@@ -1430,10 +1435,12 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
 	int timingSlot = -1;
 	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
-	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself; the other two stage locally and
-	 * their rows are pushed to the peers afterwards (light.cu dn_push_staging_kernel) */
+	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself, and so does the persistent kernel
+	 * (4-byte stores as its lanes finish, but overlapped with its ray tracing: measured faster at 8 replicas than a push afterwards,
+	 * 302 vs 349 ns per 4 requests on config 3); the wavefront kernels stage locally and their rows are pushed to the peers
+	 * afterwards (light.cu dn_push_staging_kernel: 323 -> 261 ns at 4 replicas) */
 	DnbStagingTargets allPeers = targets;
-	const bool pushAfter = v->peerAttached && kernel != 0 && targets.count > 1;
+	const bool pushAfter = v->peerAttached && kernel == 2 && targets.count > 1;
 	if(pushAfter)
 	{
 		targets.count = 1;

@@ -482,11 +482,11 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 	return cudaGetLastError();
 }
 
-/* Multi-GPU, persistent / wavefront kernels: their lanes finish voxels one at a time, so storing each voxel's three words straight
- * into every replica means 4-byte stores scattered over NVLink (one packet each; measured: the wavefront kernels 45 % slower at 4
- * replicas than at 1).  Those kernels therefore stage into their own replica only, and this kernel then pushes the rows of the CTAs
- * the replica owns (4 requests = 1536 contiguous bytes each) to the other replicas with coalesced 16-byte stores.  (The
- * warp-per-request kernel keeps its fused 128-byte row stores: its dispatches are latency-critical.) */
+/* Multi-GPU, wavefront kernels: their serve kernel finishes voxels one at a time, so storing each voxel's three words straight into
+ * every replica means 4-byte stores scattered over NVLink (one packet each; measured 45 % slower at 4 replicas than at 1).  They
+ * therefore stage into their own replica only, and this kernel then pushes the rows of the CTAs the replica owns (4 requests = 1536
+ * contiguous bytes each) to the other replicas with coalesced 16-byte stores.  (The warp-per-request kernel keeps its fused 128-byte
+ * row stores, and the persistent kernel its per-voxel stores, which overlap with its ray tracing.) */
 __global__ void __launch_bounds__(128) dn_push_staging_kernel(const uint4* __restrict__ own, DnbStagingTargets T, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests)
 {
 	for(uint32_t k = blockIdx.x; k < numCtas; k += gridDim.x)
