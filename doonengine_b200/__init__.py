@@ -182,6 +182,7 @@ _PROTOTYPES = {
     "DN_b200_read_counters": (C.c_bool, [C.POINTER(DNvolume), C.POINTER(DNb200counters), C.c_bool]),
     "DN_b200_get_stats": (None, [C.POINTER(DNvolume), C.POINTER(DNb200stats)]),
     "DN_b200_enable_timing": (None, [C.c_bool]),
+    "DN_b200_kernel_launches": (C.c_uint64, []),
     "DN_b200_touch_tile": (None, [C.POINTER(DNvolume), DNivec3]),
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
     "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),

@@ -144,7 +144,7 @@ extern "C" cudaError_t dnb_launch_or_bits(uint32_t* dst, const uint32_t* src, ui
 {
 	if(words == 0)
 		return cudaSuccess;
-	dn_or_bits_kernel<<<(words + 255) / 256, 256, 0, stream>>>(dst, src, words);
+	{ DNB_LAUNCHED(1); dn_or_bits_kernel<<<(words + 255) / 256, 256, 0, stream>>>(dst, src, words); }
 	return cudaGetLastError();
 }
 
@@ -157,8 +157,8 @@ extern "C" cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uin
                                                 uint32_t* grandTotal, cudaStream_t stream)
 {
 	const uint32_t blocks = dnb_compact_num_blocks(scene->numTiles);
-	dn_compact_kernel<false><<<blocks, COMPACT_WARPS * 32, 0, stream>>>(scene->visible, forced, scene->tileSlot, scene->slots, scene->numTiles, split, frameNum, blockCounts, nullptr, nullptr);
-	dn_scan_blocks_kernel<<<1, 1024, 0, stream>>>(blockCounts, blockOffsets, blocks, grandTotal);
+	{ DNB_LAUNCHED(1); dn_compact_kernel<false><<<blocks, COMPACT_WARPS * 32, 0, stream>>>(scene->visible, forced, scene->tileSlot, scene->slots, scene->numTiles, split, frameNum, blockCounts, nullptr, nullptr); }
+	{ DNB_LAUNCHED(1); dn_scan_blocks_kernel<<<1, 1024, 0, stream>>>(blockCounts, blockOffsets, blocks, grandTotal); }
 	return cudaGetLastError();
 }
 
@@ -166,7 +166,7 @@ extern "C" cudaError_t dnb_launch_compact_write(const DnbScene* scene, const uin
                                                 cudaStream_t stream)
 {
 	const uint32_t blocks = dnb_compact_num_blocks(scene->numTiles);
-	dn_compact_kernel<true><<<blocks, COMPACT_WARPS * 32, 0, stream>>>(scene->visible, forced, scene->tileSlot, scene->slots, scene->numTiles, split, frameNum, nullptr, blockOffsets, requests);
+	{ DNB_LAUNCHED(1); dn_compact_kernel<true><<<blocks, COMPACT_WARPS * 32, 0, stream>>>(scene->visible, forced, scene->tileSlot, scene->slots, scene->numTiles, split, frameNum, nullptr, blockOffsets, requests); }
 	return cudaGetLastError();
 }
 
@@ -174,6 +174,6 @@ extern "C" cudaError_t dnb_launch_set_bits(uint32_t* bits, const uint32_t* tiles
 {
 	if(n == 0)
 		return cudaSuccess;
-	dn_set_bits_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bits, tiles, n);
+	{ DNB_LAUNCHED(1); dn_set_bits_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bits, tiles, n); }
 	return cudaGetLastError();
 }

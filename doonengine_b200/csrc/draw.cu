@@ -195,8 +195,8 @@ extern "C" cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParam
 	p.rowStride = stride;
 	dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(groups * 2));
 	if(scene->counters)
-		dn_draw_kernel<true><<<grid, 256, 0, stream>>>(*scene, p, image, mirror, hits);
+		{ DNB_LAUNCHED(1); dn_draw_kernel<true><<<grid, 256, 0, stream>>>(*scene, p, image, mirror, hits); }
 	else
-		dn_draw_kernel<false><<<grid, 256, 0, stream>>>(*scene, p, image, mirror, hits);
+		{ DNB_LAUNCHED(1); dn_draw_kernel<false><<<grid, 256, 0, stream>>>(*scene, p, image, mirror, hits); }
 	return cudaGetLastError();
 }

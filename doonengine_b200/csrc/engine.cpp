@@ -24,6 +24,7 @@ namespace dnb
 {
 
 static Context g_ctx;
+
 Context& ctx() { return g_ctx; }
 static int g_requestedDevice = -1;
 
@@ -785,6 +786,8 @@ static void sync_read(VolumeImpl* v, uint32_t split)
 
 using namespace dnb;
 
+extern "C" { unsigned long long g_dnbKernelLaunches = 0; }
+
 /* ------------------------------------------------------------------------------------------------ */
 
 extern "C" int DN_b200_device_count(void)
@@ -898,6 +901,7 @@ extern "C" bool DN_b200_synchronize(void)
 	return cuda_ok(cudaStreamSynchronize(c.stream()), "synchronize") && ok;
 }
 
+extern "C" uint64_t DN_b200_kernel_launches(void) { return g_dnbKernelLaunches; }
 extern "C" void DN_b200_enable_timing(bool enable) { ctx().timing = enable; }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -18,6 +18,10 @@ typedef struct DnbUploadItem
 extern "C" {
 #endif
 
+/* kernels this library has launched since it was loaded (every launch wrapper counts; read with DN_b200_kernel_launches) */
+extern unsigned long long g_dnbKernelLaunches;
+#define DNB_LAUNCHED(n) (g_dnbKernelLaunches += (n))
+
 /* mirror: second destination of every pixel (peer memory of the root replica), or NULL */
 cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, float4* mirror, DnbHit* hits, cudaStream_t stream);
 

@@ -449,7 +449,7 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 	if(numRequests == 0 || numCtas == 0)
 		return cudaSuccess;
 	if(scene->counters)
-		dn_light_kernel<true><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets);
+		{ DNB_LAUNCHED(1); dn_light_kernel<true><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets); }
 	else if(flatCounter)
 	{
 		/* persistent warps: enough CTAs to fill the machine, each lane pulls voxels from the work counter */
@@ -475,10 +475,10 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 			tuning.endLanes = knob("DN_B200_FLAT_END", 28);
 			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 16);
 		}
-		dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, numCtas * 128u, flatCounter, *targets, tuning);
+		{ DNB_LAUNCHED(1); dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, numCtas * 128u, flatCounter, *targets, tuning); }
 	}
 	else
-		dn_light_kernel<false><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets);
+		{ DNB_LAUNCHED(1); dn_light_kernel<false><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets); }
 	return cudaGetLastError();
 }
 
@@ -513,7 +513,7 @@ extern "C" cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, u
 	if(numCtas == 0 || numRequests == 0 || peers->count < 2)
 		return cudaSuccess;
 	const uint32_t grid = numCtas < 148u * 16u ? numCtas : 148u * 16u;
-	dn_push_staging_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(peers->dst[self]), *peers, self, firstCta, ctaStride, numCtas, numRequests);
+	{ DNB_LAUNCHED(1); dn_push_staging_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(peers->dst[self]), *peers, self, firstCta, ctaStride, numCtas, numRequests); }
 	return cudaGetLastError();
 }
 
@@ -532,15 +532,15 @@ extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, 
 			maxCtas = sms * 8;
 		}
 		const uint32_t ctas = std::min<uint32_t>((numRequests + 7) / 8, (uint32_t)maxCtas);
-		dn_commit_kernel<<<ctas, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging, litCounter);
+		{ DNB_LAUNCHED(1); dn_commit_kernel<<<ctas, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging, litCounter); }
 		cudaError_t e = cudaGetLastError();
 		if(e != cudaSuccess)
 			return e;
 	}
 	const uint32_t words = (scene->numTiles + 31) / 32;
 	if(peers)
-		dn_merge_visible_peers_kernel<<<(words + 255) / 256, 256, 0, stream>>>(*peers, scene->visible, words);
+		{ DNB_LAUNCHED(1); dn_merge_visible_peers_kernel<<<(words + 255) / 256, 256, 0, stream>>>(*peers, scene->visible, words); }
 	else
-		dn_merge_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(scene->visible, scene->propagate, words);
+		{ DNB_LAUNCHED(1); dn_merge_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(scene->visible, scene->propagate, words); }
 	return cudaGetLastError();
 }

@@ -405,12 +405,12 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 		}
 		uint32_t* now = counters + 1 + (pass & 1u);
 		uint32_t* nxt = counters + 1 + ((pass + 1u) & 1u);
-		dn_wave_serve_kernel<<<P / WAVE_SERVE_THREADS, WAVE_SERVE_THREADS, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, totalItems, counters, *targets, ctx, P, now, nxt);
+		{ DNB_LAUNCHED(1); dn_wave_serve_kernel<<<P / WAVE_SERVE_THREADS, WAVE_SERVE_THREADS, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, totalItems, counters, *targets, ctx, P, now, nxt); }
 		if((e = cudaMemcpyAsync(&g_wave.pinned[pass & 7u], now, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
 			return e;
 		if((e = cudaEventRecord(g_wave.ev[pass & 7u], stream)) != cudaSuccess)
 			return e;
-		dn_wave_step_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters + 3, tuning);
+		{ DNB_LAUNCHED(1); dn_wave_step_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters + 3, tuning); }
 		if((e = cudaGetLastError()) != cudaSuccess)
 			return e;
 	}

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) dn_peer_or_visible_kernel(DnbPeerTable T,
 
 extern "C" cudaError_t dnb_launch_peer_barrier(const DnbPeerTable* peers, uint32_t epoch, uint32_t* status, cudaStream_t stream)
 {
-	dn_peer_barrier_kernel<<<1, 32, 0, stream>>>(*peers, epoch, status);
+	{ DNB_LAUNCHED(1); dn_peer_barrier_kernel<<<1, 32, 0, stream>>>(*peers, epoch, status); }
 	return cudaGetLastError();
 }
 
@@ -94,6 +94,6 @@ extern "C" cudaError_t dnb_launch_peer_or_visible(const DnbPeerTable* peers, uin
 {
 	if(words == 0)
 		return cudaSuccess;
-	dn_peer_or_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(*peers, visible, words);
+	{ DNB_LAUNCHED(1); dn_peer_or_visible_kernel<<<(words + 255) / 256, 256, 0, stream>>>(*peers, visible, words); }
 	return cudaGetLastError();
 }

@@ -87,6 +87,6 @@ extern "C" cudaError_t dnb_launch_pick(const DnbScene* scene, const float* dirs,
 {
 	if(count == 0)
 		return cudaSuccess;
-	dn_pick_kernel<<<(count + 127u) / 128u, 128, 0, stream>>>(*scene, dirs, origins, count, maxSteps, out);
+	{ DNB_LAUNCHED(1); dn_pick_kernel<<<(count + 127u) / 128u, 128, 0, stream>>>(*scene, dirs, origins, count, maxSteps, out); }
 	return cudaGetLastError();
 }

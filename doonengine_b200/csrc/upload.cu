@@ -56,6 +56,6 @@ extern "C" cudaError_t dnb_launch_scatter(const DnbUploadItem* items, const DnbS
 {
 	if(numItems == 0)
 		return cudaSuccess;
-	dn_scatter_chunks_kernel<<<(numItems + 7) / 8, 256, 0, stream>>>(items, headers, blobRecords, numItems, mapSize[0], mapSize[1], blocks[0], blocks[1], tileSlot, occ64, visible, slots, records);
+	{ DNB_LAUNCHED(1); dn_scatter_chunks_kernel<<<(numItems + 7) / 8, 256, 0, stream>>>(items, headers, blobRecords, numItems, mapSize[0], mapSize[1], blocks[0], blocks[1], tileSlot, occ64, visible, slots, records); }
 	return cudaGetLastError();
 }

@@ -101,7 +101,8 @@ typedef struct DNb200stats
 	uint32_t lastWavePasses;                                /* serve + step passes the last wavefront dispatch queued */
 } DNb200stats;
 void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
-void DN_b200_enable_timing(bool enable); /* record CUDA events around each kernel group (adds a sync when read) */
+void DN_b200_enable_timing(bool enable);
+uint64_t DN_b200_kernel_launches(void); /* CUDA kernels this library has launched since it was loaded (all volumes) */ /* record CUDA events around each kernel group (adds a sync when read) */
 
 /* tiles whose host-side state was changed WITHOUT going through a DN_* call (e.g. writing vol->chunks[i].voxels
  * directly and setting .updated) must be announced, because DN_sync_gpu does not scan the whole map */
