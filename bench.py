@@ -337,37 +337,50 @@ def run_ours(args, scene, tiles, res, desc):
     if args.config == "c4":
         edit_stream = [frame_edits(k, tiles) for k in range(args.warmup + 2 * args.steps + 1)]
 
+    host_s = {"edits": 0.0, "draw": 0.0, "read_back_enqueue": 0.0, "sync": 0.0, "light_compute": 0.0, "commit": 0.0, "wait_read": 0.0, "steps": 0}
+
     def step(k, timed, read_back):
-        """one frame; returns the events bracketing its phases."""
+        """one frame; returns the events bracketing its phases.  host_s accumulates the HOST time spent inside each API call
+        (DN_sync_gpu blocks until the request count is back, so its share is mostly the device catching up)."""
         marks = [ev() for _ in range(6)] if timed else None
         fb = fbs[k % 3]
+        t0 = time.perf_counter()
         if edit_stream is not None:
-            t_e = time.perf_counter()
             e.set_voxels(*edit_stream[k])
-            edit_host_s[0] += time.perf_counter() - t_e
+            edit_host_s[0] += time.perf_counter() - t0
+        t1 = time.perf_counter()
         if timed:
             marks[0].record(stream)
         sh.draw(fb, view, proj)
+        t2 = time.perf_counter()
         if read_back:
             # the copy of this replica's rows to pinned host memory runs on a side stream, overlapped with compaction, lighting
             # and the next draw
             L.DN_b200_read_framebuffer_rows_async(fb, e.vol, host_ptrs[k % 3], fb_bytes)
+        t3 = time.perf_counter()
         if timed:
             marks[1].record(stream)
         L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
+        t4 = time.perf_counter()
         if timed:
             marks[2].record(stream)
         sh.light_compute(1, 1000, frame_time(k))
+        t5 = time.perf_counter()
         if timed:
             marks[3].record(stream)
         sh.light_exchange()
         sh.light_commit()
+        t6 = time.perf_counter()
         if timed:
             marks[4].record(stream)
         if read_back:
             L.DN_b200_wait_framebuffer_read(fbs[(k - 1) % 3])  # frame k-1's pixels are on the host
+        t7 = time.perf_counter()
         if timed:
             marks[5].record(stream)
+        for key, dt in (("edits", t1 - t0), ("draw", t2 - t1), ("read_back_enqueue", t3 - t2), ("sync", t4 - t3), ("light_compute", t5 - t4), ("commit", t6 - t5), ("wait_read", t7 - t6)):
+            host_s[key] += dt
+        host_s["steps"] += 1
         return marks, int(e.vol.contents.numLightingRequests)
 
     def barrier():
@@ -388,8 +401,9 @@ def run_ours(args, scene, tiles, res, desc):
         region0.record(stream)
         for i in range(steps):
             flush.fill_(i & 0xFF)
-            m, r = step(k0 + i, True, read_back)
-            all_marks.append(m)
+            m, r = step(k0 + i, not read_back, read_back)  # the end-to-end region is timed as ONE piece: no per-phase events inside it
+            if m is not None:
+                all_marks.append(m)
             reqs += r
         drain0, drain1 = ev(), ev()
         drain0.record(stream)
@@ -428,6 +442,8 @@ def run_ours(args, scene, tiles, res, desc):
     launches0 = int(L.DN_b200_kernel_launches())
     phases, lit, reqs, clocks, wall = run_loop(args.warmup, args.steps, False)
     # ---- timed region 2: end to end through the API incl. framebuffer read-back into pinned host memory ----
+    for key in host_s:
+        host_s[key] = 0
     phases2, lit2, reqs2, clocks2, wall2 = run_loop(args.warmup + args.steps, args.steps, True)
     launches = int(L.DN_b200_kernel_launches()) - launches0  # this rank's kernels in both timed regions, counted by the library's launch wrappers
 
@@ -523,6 +539,7 @@ def run_ours(args, scene, tiles, res, desc):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8192 + 2416, "d2h_bytes_per_step": fb_bytes + 4, "ms_per_step": frame2_ms,
                     "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps frame k+1; N > 1: every replica copies the rows it drew into one shared pinned mapping); timed as ONE region from the first draw to the last copy landing, L2 flushes and host gaps between steps included"},
             "gpu_launches": launches,
+            "host_ms_per_step_e2e": {k_: (1000.0 * v_ / max(host_s["steps"], 1)) for k_, v_ in host_s.items() if k_ != "steps"},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         if edits:

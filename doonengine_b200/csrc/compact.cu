@@ -13,8 +13,8 @@
  *                             request count.  Per-CTA totals (256 tiles) go to blockCounts[].
  *   dn_scan_blocks_kernel     one CTA: exclusive scan of blockCounts[] and the grand total.
  *   dn_compact_kernel<true>   same walk, writing the request words at their final offsets.
- * The host reads the total back in between (DNvolume::numLightingRequests is public) and grows the request
- * buffer if needed.  Traffic: numTiles/8 bytes of bitmap + 4 B tileSlot + 8 B slot fields per VISIBLE tile
+ * The scan kernel also stores the total into a pinned host word (DNvolume::numLightingRequests is public, and the host sizes
+ * the lighting dispatch from it).  Traffic: numTiles/8 bytes of bitmap + 4 B tileSlot + 8 B slot fields per VISIBLE tile
  * + 4 B per request; HBM/L2-streaming bound.
  */
 #include "kernels.h"
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(COMPACT_WARPS * 32) dn_compact_kernel(const ui
 }
 
 /* exclusive scan of blockCounts[0..n) by one CTA of 1024 threads; total -> *grandTotal */
-__global__ void __launch_bounds__(1024) dn_scan_blocks_kernel(const uint32_t* __restrict__ blockCounts, uint32_t* __restrict__ blockOffsets, uint32_t n, uint32_t* __restrict__ grandTotal)
+__global__ void __launch_bounds__(1024) dn_scan_blocks_kernel(const uint32_t* __restrict__ blockCounts, uint32_t* __restrict__ blockOffsets, uint32_t n, uint32_t* __restrict__ grandTotal,
+                                                              volatile uint32_t* hostTotal)
 {
 	__shared__ uint32_t s_warp[32];
 	__shared__ uint32_t s_carry;
@@ -117,7 +118,16 @@ __global__ void __launch_bounds__(1024) dn_scan_blocks_kernel(const uint32_t* __
 		__syncthreads();
 	}
 	if(threadIdx.x == 0)
+	{
 		*grandTotal = s_carry;
+		if(hostTotal)
+		{
+			/* straight into the host's pinned word (zero-copy store): a 4-byte cudaMemcpyAsync here queued behind the 33 MB
+			 * framebuffer read-back on the copy engine and kept DN_sync_gpu waiting 0.5 ms per frame */
+			*hostTotal = s_carry;
+			__threadfence_system();
+		}
+	}
 }
 
 /* forced[] |= bit(tile) for a list of tiles whose chunk has pending edits (voxel.c:1470) */
@@ -154,11 +164,11 @@ extern "C" uint32_t dnb_compact_num_blocks(uint32_t numTiles)
 }
 
 extern "C" cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets,
-                                                uint32_t* grandTotal, cudaStream_t stream)
+                                                uint32_t* grandTotal, uint32_t* hostTotal, cudaStream_t stream)
 {
 	const uint32_t blocks = dnb_compact_num_blocks(scene->numTiles);
 	{ DNB_LAUNCHED(1); dn_compact_kernel<false><<<blocks, COMPACT_WARPS * 32, 0, stream>>>(scene->visible, forced, scene->tileSlot, scene->slots, scene->numTiles, split, frameNum, blockCounts, nullptr, nullptr); }
-	{ DNB_LAUNCHED(1); dn_scan_blocks_kernel<<<1, 1024, 0, stream>>>(blockCounts, blockOffsets, blocks, grandTotal); }
+	{ DNB_LAUNCHED(1); dn_scan_blocks_kernel<<<1, 1024, 0, stream>>>(blockCounts, blockOffsets, blocks, grandTotal, hostTotal); }
 	return cudaGetLastError();
 }
 

@@ -765,11 +765,14 @@ static void sync_read(VolumeImpl* v, uint32_t split)
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing lighting request buffer to accomodate %zu requests (%zu bytes)", cap, cap * sizeof(uint32_t));
 		device_reserve(v->requests, cap, false, false, "lighting requests");
 	}
-	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, s), "compaction count");
-	cuda_ok(cudaMemcpyAsync(v->pinnedScalars, v->scalars.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "request count read-back");
+	/* the count kernel stores the total straight into the pinned host word; the host waits for THAT kernel only (an event), not for
+	 * a copy-engine transfer that would queue behind a framebuffer read-back, and not for the write pass */
+	Context& cx = ctx();
+	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, v->pinnedScalars, s), "compaction count");
+	cuda_ok(cudaEventRecord(cx.evCountDone, s), "event record");
 	cuda_ok(dnb_launch_compact_write(&scene, forced, split, vol->frameNum, v->blockOffsets.ptr, v->requests.ptr, s), "compaction write");
-	cuda_ok(cudaStreamSynchronize(s), "compaction");
-	const size_t total = v->pinnedScalars[0];
+	cuda_ok(cudaEventSynchronize(cx.evCountDone), "compaction");
+	const size_t total = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars);
 
 	if(forced)
 	{
@@ -844,6 +847,7 @@ extern "C" bool DN_init(void)
 	ok = ok && cuda_ok(cudaStreamCreateWithFlags(&c.uploadStream, cudaStreamNonBlocking), "stream create");
 	ok = ok && cuda_ok(cudaStreamCreateWithFlags(&c.readStream, cudaStreamNonBlocking), "stream create");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evDrawDone, cudaEventDisableTiming), "event create");
+	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evCountDone, cudaEventDisableTiming), "event create");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evReadDone, cudaEventDisableTiming), "event create");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evUploadDone, cudaEventDisableTiming), "event create");
 	ok = ok && cuda_ok(cudaEventCreateWithFlags(&c.evComputeDone, cudaEventDisableTiming), "event create");
@@ -878,7 +882,7 @@ extern "C" void DN_quit(void)
 	cudaStreamDestroy(c.ownStream);
 	cudaStreamDestroy(c.uploadStream);
 	cudaStreamDestroy(c.readStream);
-	cudaEventDestroy(c.evDrawDone); cudaEventDestroy(c.evReadDone);
+	cudaEventDestroy(c.evDrawDone); cudaEventDestroy(c.evReadDone); cudaEventDestroy(c.evCountDone);
 	c.ownStream = c.uploadStream = nullptr;
 	c.ready = false;
 }
@@ -1028,9 +1032,19 @@ extern "C" bool DN_b200_read_framebuffer_rows_async(GLuint id, DNvolume* vol, fl
 	const int count = end > begin ? (end - begin + stride - 1) / stride : 0;
 	if(ok && count > 0)
 	{
-		const size_t at = (size_t)begin * groupBytes;
-		ok = cuda_ok(cudaMemcpy2DAsync((char*)dst + at, groupBytes * stride, (const char*)fb->image + at, groupBytes * stride, groupBytes, (size_t)count, cudaMemcpyDeviceToHost, c.readStream),
-		             "framebuffer rows read");
+		/* plain 1-D copies: one for a contiguous band, one per 16-pixel group row for interleaved rows.  (cudaMemcpy2DAsync moved the
+		 * same bytes at 24 GB/s on these boxes, a 1-D copy at 55 GB/s: tools/d2h_probe.py; the read-back bounds the end-to-end frame) */
+		if(stride == 1)
+		{
+			const size_t at = (size_t)begin * groupBytes;
+			ok = cuda_ok(cudaMemcpyAsync((char*)dst + at, (const char*)fb->image + at, groupBytes * (size_t)count, cudaMemcpyDeviceToHost, c.readStream), "framebuffer rows read");
+		}
+		else
+			for(int g = begin; g < end && ok; g += stride)
+			{
+				const size_t at = (size_t)g * groupBytes;
+				ok = cuda_ok(cudaMemcpyAsync((char*)dst + at, (const char*)fb->image + at, groupBytes, cudaMemcpyDeviceToHost, c.readStream), "framebuffer rows read");
+			}
 	}
 	ok = ok && cuda_ok(cudaEventRecord(c.evReadDone, c.readStream), "event record");
 	if(ok && !fb->evRead)

@@ -39,7 +39,7 @@ struct Context
 	cudaStream_t ownStream = nullptr;    /* kernels */
 	cudaStream_t uploadStream = nullptr; /* host->device copies of edited chunks + their scatter */
 	cudaStream_t readStream = nullptr;   /* asynchronous framebuffer read-back */
-	cudaEvent_t  evDrawDone = nullptr, evReadDone = nullptr;
+	cudaEvent_t  evDrawDone = nullptr, evReadDone = nullptr, evCountDone = nullptr;
 	cudaStream_t userStream = nullptr;   /* DN_b200_set_stream */
 	bool         useUserStream = false;
 	cudaEvent_t  evUploadDone = nullptr, evComputeDone = nullptr;

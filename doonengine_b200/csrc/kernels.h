@@ -53,8 +53,9 @@ cudaError_t dnb_launch_peer_barrier(const DnbPeerTable* peers, uint32_t epoch, u
 cudaError_t dnb_launch_peer_or_visible(const DnbPeerTable* peers, uint32_t* visible, uint32_t words, cudaStream_t stream);
 
 uint32_t    dnb_compact_num_blocks(uint32_t numTiles);
+/* hostTotal: NULL or a device-accessible pinned host word that also receives the total (zero-copy store) */
 cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets, uint32_t* grandTotal,
-                                     cudaStream_t stream);
+                                     uint32_t* hostTotal, cudaStream_t stream);
 cudaError_t dnb_launch_compact_write(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, const uint32_t* blockOffsets, uint32_t* requests, cudaStream_t stream);
 cudaError_t dnb_launch_set_bits(uint32_t* bits, const uint32_t* tiles, uint32_t n, cudaStream_t stream);
 
