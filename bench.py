@@ -103,21 +103,31 @@ class ClockSampler(threading.Thread):
         self.sm_max = None
         self.power = []
         self.stop_flag = False
-
-    def run(self):
+        self.nv = self.handle = None
+        # NVML is loaded and initialised HERE, on the caller's thread and before anything is timed: done inside run() it competed
+        # with the frame loop for the interpreter during the first timed steps
         try:
             import pynvml as nv
             nv.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(visible.split(",")[self.index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            self.handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            self.nv = nv
+        except Exception as ex:  # NVML missing: report no clocks rather than fail the benchmark
+            self.error = repr(ex)
+
+    def run(self):
+        nv, h = self.nv, self.handle
+        if nv is None:
+            return
+        try:
             while not self.stop_flag:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for n, bit in names.items():
+                for n, bit in self.names.items():
                     if mask & bit:
                         self.reasons.add(n)
                 try:
@@ -125,7 +135,7 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     pass
                 time.sleep(self.period_s)
-        except Exception as ex:  # NVML missing: report no clocks rather than fail the benchmark
+        except Exception as ex:
             self.error = repr(ex)
 
     def finish(self):
@@ -391,8 +401,8 @@ def run_ours(args, scene, tiles, res, desc):
     def run_loop(k0, steps, read_back):
         """K timed steps, L2 flushed (untimed) between them; returns per-phase ms sums, voxels lit, requests."""
         lit0 = e.stats()["voxelsLit"]
+        sampler = ClockSampler(local, args.sampler_ms / 1000.0) if args.sampler_ms > 0 else None
         barrier()
-        sampler = ClockSampler(local, args.sampler_ms / 1000.0)
         if args.sampler_ms > 0:
             sampler.start()
         all_marks, reqs = [], 0
