@@ -67,13 +67,13 @@ DNB_FN f3 vox_diffuse(uint4 v)
 DNB_FN DnbMaterial load_material(const DnbScene& S, uint32_t id)
 {
 	const uint4* p = reinterpret_cast<const uint4*>(S.materials + id);
-	uint4 a = __ldg(p), b = __ldg(p + 1);
+	uint4 a = DNB_LDG(p), b = DNB_LDG(p + 1);
 	DnbMaterial m;
 	m.pad[0] = m.pad[1] = 0.0f;
 	m.emissive = a.z;
-	m.opacity = __uint_as_float(a.w);
-	m.refractIndex = __uint_as_float(b.x);
-	m.specular = __uint_as_float(b.y);
+	m.opacity = DNB_U2F(a.w);
+	m.refractIndex = DNB_U2F(b.x);
+	m.specular = DNB_U2F(b.y);
 	m.reflectType = b.z;
 	m.shininess = b.w;
 	return m;
@@ -215,7 +215,7 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 				              (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0)))
 					break;
 				blk.x = m.pos.x & ~3; blk.y = m.pos.y & ~3; blk.z = m.pos.z & ~3;
-				occWord = __ldg(S.occ64 + ((uint32_t)(m.pos.x >> 2) + S.blocks[0] * ((uint32_t)(m.pos.y >> 2) + S.blocks[1] * (uint32_t)(m.pos.z >> 2))));
+				occWord = DNB_LDG(S.occ64 + ((uint32_t)(m.pos.x >> 2) + S.blocks[0] * ((uint32_t)(m.pos.y >> 2) + S.blocks[1] * (uint32_t)(m.pos.z >> 2))));
 			}
 			else if(COUNT && !in_map_bounds(S, m.pos))
 				break;
@@ -256,7 +256,7 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 		/* ---- phase B: cross the resident chunk voxel by voxel ---- */
 		{
 			const uint32_t mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
-			const DnbSlot* slot = S.slots + (__ldg(S.tileSlot + mapIndex) - 1u);
+			const DnbSlot* slot = S.slots + (DNB_LDG(S.tileSlot + mapIndex) - 1u);
 			DNB_COUNT(chunks);
 
 			/* SH:443-445: entry point in chunk-local voxel units */
@@ -274,7 +274,7 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 			uint32_t wordIdx = 0xFFFFFFFFu, word = 0;
 			uint32_t bias = 0, offp = 0; /* exact chunk cull (see cull_offsets): c.pos is shifted by the offsets in offp */
 			if(!COUNT && st.lastVoxID == 255u)
-				offp = cull_offsets(__ldg(&slot->bbox), c.step, c.pos, bias);
+				offp = cull_offsets(DNB_LDG(&slot->bbox), c.step, c.pos, bias);
 			while(in_chunk_bounds(c.pos))
 			{
 				if(++cguard > DNB_MAX_CHUNK_STEPS)
@@ -288,14 +288,14 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 				if((local >> 5) != wordIdx)
 				{
 					wordIdx = local >> 5;
-					word = __ldg(slot->mask + wordIdx);
+					word = DNB_LDG(slot->mask + wordIdx);
 				}
 
 				if(((word >> (local & 31u)) & 1u) && !ignoreFirst)
 				{
 					/* SH:150-169 with per-word prefix counts instead of quarter counts */
-					const uint32_t rel = (uint32_t)__ldg(slot->prefix + wordIdx) + __popc(word & ((1u << (local & 31u)) - 1u));
-					const uint4 rec = __ldg(S.records + (__ldg(&slot->voxelBase) + rel));
+					const uint32_t rel = (uint32_t)DNB_LDG(slot->prefix + wordIdx) + DNB_POPC(word & ((1u << (local & 31u)) - 1u));
+					const uint4 rec = DNB_LDG(S.records + (DNB_LDG(&slot->voxelBase) + rel));
 					DNB_COUNT(records);
 					st.vox = rec;
 

@@ -11,7 +11,26 @@
 struct f3 { float x, y, z; };
 struct i3 { int x, y, z; };
 
+/* A host harness (tools/proto) may define DNB_FN as __host__ __device__ to run the traversal code on the CPU; the read-only-load and
+ * bit intrinsics go through these wrappers for the same reason (device code is unchanged by them). */
+#ifndef DNB_FN
 #define DNB_FN __device__ __forceinline__
+#endif
+#ifdef __CUDA_ARCH__
+#define DNB_LDG(p) __ldg(p)
+#define DNB_POPC(x) __popc(x)
+#define DNB_U2F(x) __uint_as_float(x)
+#define DNB_F2U(x) __float_as_uint(x)
+#else
+#include <string.h>
+template <typename T> static inline T dnb_host_load(const T* p) { return *p; }
+static inline float dnb_host_u2f(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned dnb_host_f2u(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+#define DNB_LDG(p) dnb_host_load(p)
+#define DNB_POPC(x) __builtin_popcount(x)
+#define DNB_U2F(x) dnb_host_u2f(x)
+#define DNB_F2U(x) dnb_host_f2u(x)
+#endif
 
 DNB_FN f3 mk3(float x, float y, float z)  { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 DNB_FN f3 splat3(float s)                 { return mk3(s, s, s); }
