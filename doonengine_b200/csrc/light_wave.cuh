@@ -347,7 +347,7 @@ static DnbWaveHost g_wave;
 
 extern "C" size_t dnb_wave_slot_bytes(void) { return (size_t)WAVE_PLANES * sizeof(uint4); }
 
-/* ctx: WAVE_PLANES * P uint4, P a multiple of 256; counters: 4 device words (work counter, two live-slot counters, spare) */
+/* ctx: WAVE_PLANES * P uint4, P a multiple of 256; counters: 4 device words (work counter, two live-slot counters used alternately, slot cursor of the step kernel) */
 extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
                                              const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream)
 {
