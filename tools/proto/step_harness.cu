@@ -89,4 +89,63 @@ extern "C" int harness_run(const DnbScene* scene, const RayIn* rays, uint32_t co
 	return 0;
 }
 
+/* the unified stepper's per-ray sequence of operations, for the warp-scheduling model (tools/proto/schedule_model.py):
+ * 0 cheap step at the tile level, 1 cheap step at the voxel level, 2 one iteration of the empty-block fast loop, 3 tile-level block
+ * change, 4 next z-layer of a chunk, 5 chunk exit, 6 chunk entry, 7 opaque hit, 8 transparent voxel; 255-terminated, `cap` bytes per ray */
+extern "C" int harness_trace(const DnbScene* scene, const RayIn* rays, uint32_t count, uint8_t* ops, uint32_t cap)
+{
+	const DnbScene S = *scene;
+	for(uint32_t i = 0; i < count; i++)
+	{
+		const RayIn& r = rays[i];
+		uint8_t* out = ops + (size_t)i * cap;
+		uint32_t n = 0;
+		auto put = [&](uint8_t c) { if(n + 1 < cap) out[n++] = c; };
+		UniLane L;
+		ray_state_reset(L.st);
+		L.st.lastVoxID = r.lastVoxID;
+		L.st.lastVoxRefract = r.lastVoxRefract;
+		L.dir = mk3(r.dir[0], r.dir[1], r.dir[2]);
+		L.inv = rcp3(L.dir);
+		L.rayPos = mk3(r.pos[0], r.pos[1], r.pos[2]);
+		L.ignoreFirst = r.ignoreFirst != 0;
+		uint32_t state, guard = 0;
+		uni_start(L, state);
+		while(state != U_END && ++guard < 1000000u)
+		{
+			const uint32_t lv = L.lv;
+			if(state == U_STEP)
+			{
+				const uint32_t g0 = L.g;
+				uni_step(S, L, state);
+				if(state == U_STEP || state == U_END)
+				{
+					/* a completed iteration (or a guard trip); the fast loop shows as g advancing by more than one */
+					put(lv ? 1 : 0);
+					for(uint32_t k = g0 + 2; k <= L.g && lv == 0; k++)
+						put(2);
+				}
+			}
+			else if(state == U_BOUNDARY)
+			{
+				const bool leaves = lv != 0 && !in_chunk_bounds(L.pos);
+				uni_boundary(S, L, state);
+				put(lv == 0 ? 3 : (leaves ? 5 : 4));
+			}
+			else if(state == U_ENTER)
+			{
+				uni_enter(S, L, state);
+				put(6);
+			}
+			else
+			{
+				uni_hit(S, L, state);
+				put(state == U_END ? 7 : 8);
+			}
+		}
+		out[n] = 255;
+	}
+	return 0;
+}
+
 extern "C" size_t harness_sizes(int which) { return which == 0 ? sizeof(DnbScene) : which == 1 ? sizeof(RayIn) : sizeof(RayOut); }
