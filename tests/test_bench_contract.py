@@ -1,0 +1,41 @@
+"""bench.py's contract, as far as it can be exercised without a GPU: the reference arm (`--impl reference`: the reference's own host code
+driving the CPU restatement of its shaders) prints ONE JSON line with the keys the driver reads, and the GPU arm refuses to run -- loudly,
+without falling back to anything -- when there is no CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+
+
+def test_reference_arm_json_line():
+    p = _run("--impl", "reference", "--config", "small", "--steps", "2", "--warmup", "3")
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "voxel_lighting_updates_per_s" and d["unit"] == "voxel-updates/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 3 and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    e2e = d["e2e"]
+    assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0 and 0 < e2e["value"] <= d["value"] and e2e["unit"] == d["unit"]
+    assert "workload" in d["config"]
+
+
+def test_gpu_arm_has_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = _run("--config", "small", "--steps", "1", "--warmup", "3")
+    assert p.returncode != 0
+    assert "no CUDA device" in (p.stderr + p.stdout)
+    assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
