@@ -1251,12 +1251,13 @@ static int light_kernel_choice()
 extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = (which >= 0 && which <= 3) ? which : 2; }
 extern "C" int DN_b200_get_light_kernel(void) { return light_kernel_choice(); }
 
-/* Auto mode.  The two kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a
+/* Auto mode.  The three kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a
  * question of speed, and that depends on the scene: short rays that end together favour one warp per request, rays of very
- * different length favour the persistent state machine (2.6x on the sparse map).  Every dispatch is bracketed by two events
- * (no synchronisation: they are read one or two dispatches later, once they have completed anyway); the first dispatches
- * alternate between the kernels (the very first one, the jitter-free first sample, is not representative and is not used),
- * then the faster one runs, and the other is re-timed every 64th dispatch in case the camera or the map has changed. */
+ * different length the persistent state machine (2.6x on the sparse map), and large dispatches of such rays the wavefront pair.
+ * Every dispatch is bracketed by two events (no synchronisation: they are read one or two dispatches later, once they have completed
+ * anyway); the first dispatches rotate through the kernels until each has two timings (the very first one, the jitter-free first
+ * sample, is not representative and is not used), then the fastest one runs, with 5 % hysteresis, and the others are re-timed in
+ * turn every 64th dispatch in case the camera or the map has changed. */
 static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, int* slotOut)
 {
 	VolumeImpl::LightTuner& t = v->tuner;
