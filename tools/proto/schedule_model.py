@@ -182,6 +182,47 @@ def simulate(ops_list, policy, keep_eighths=4, budget=24):
     return total, useful
 
 
+def simulate_pooled(ops_list, pool=256, state_cost=40):
+    """rays pooled per CTA in shared memory: a warp repeatedly takes up to 32 rays whose next operation is of the same kind (the most
+    populated kind), loads their state, runs the operation (cheap steps: a burst of up to 4), stores the state back.  Returns warp
+    instructions in total.  state_cost = shared-memory load + store of one ray's stepping state per visit."""
+    c = COST
+    total = 0
+    nxt = 0
+    n = len(ops_list)
+    rays = []          # [ops, position]
+    kind_of = {0: "s", 1: "s", 2: "s", 3: "b", 4: "b", 5: "b", 6: "e", 7: "h", 8: "h"}
+    cost_of = {"s": c["u_step"], "b": c["u_boundary"] + c["u_exit"] // 2, "e": c["u_enter"], "h": c["u_hit"]}
+    while True:
+        while len(rays) < pool and nxt < n:
+            rays.append([ops_list[nxt], 0])
+            nxt += 1
+            total += c["refill"] / 32.0
+        if not rays:
+            break
+        groups = {"s": [], "b": [], "e": [], "h": []}
+        for r in rays:
+            groups[kind_of[r[0][r[1]]]].append(r)
+        k = max(groups, key=lambda g: len(groups[g]))
+        batch = groups[k][:32]
+        total += c["trip"] + state_cost + cost_of[k]
+        for r in batch:
+            r[1] += 1
+        if k == "s":
+            for _ in range(3):  # short burst while most of the batch keeps stepping
+                still = [r for r in batch if r[1] < len(r[0]) and kind_of[r[0][r[1]]] == "s"]
+                if len(still) < (3 * len(batch)) // 4:
+                    break
+                total += cost_of["s"] + 3
+                for r in still:
+                    r[1] += 1
+        done = [r for r in rays if r[1] >= len(r[0])]
+        if done:
+            total += c["store"] * ((len(done) + 31) // 32)
+            rays = [r for r in rays if r[1] < len(r[0])]
+    return total
+
+
 def main():
     import doonengine_b200 as dn
     from doonengine_b200 import scenes
@@ -213,6 +254,8 @@ def main():
         for keep8 in (4, 6):
             total, useful = simulate(seqs, policy, keep8)
             print("%-10s keep %d/8: %.0f warp instructions per ray, %.1f lanes per executed block" % (policy, keep8, total / n, useful / max(total / 40.0, 1)))
+    for pool in (128, 256, 512):
+        print("pooled     %3d rays per CTA: %.0f warp instructions per ray" % (pool, simulate_pooled(seqs, pool) / n))
 
 
 if __name__ == "__main__":
