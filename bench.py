@@ -179,6 +179,7 @@ def cpu_baseline(scene, tiles, chunks, camera, res, budget_s=20.0, max_frames=8)
     frames as fit the time budget (at least 2; the first dispatch is the cheaper jitter-free one and is not counted)."""
     from oracle import oracle as O
     O.build()
+    O.set_num_threads(0)  # every host core, whatever OMP_NUM_THREADS the launcher exported
     w, h = res
     e = build_engine(O.OracleEngine, scene, tiles, chunks, camera)
     e.sync(1, 1)
@@ -218,23 +219,25 @@ def run_reference(args, scene, tiles, res, desc):
         return
     from oracle import oracle as O
     O.build()
+    # every host core, whatever the launcher exported (torch.distributed.run sets OMP_NUM_THREADS=1 for its workers)
+    cores = O.set_num_threads(0)
     w, h = res
+    if args.config in ("c3", "c5"):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference needs minutes per frame on the full-size %s map; its bounded sample is taken on the metric's config (c2)" % args.config}), flush=True)
+        return
     chunks, camera = make_chunks(scene, tiles) if scene != "demo" else ([], {})
     kind = "reference" if O.have_ref() else "port"
     cls = O.RefEngine if kind == "reference" else O.OracleEngine
     # the reference sizes its voxel pool as 512*minChunks/2 (voxel.c:190): twice the chunk count keeps everything resident
     e = build_engine(cls, scene, tiles, chunks, camera, min_chunks=2 * len(chunks) + 32)
     e.sync(1, 1)
-    # bounded sample: the draw runs at reduced resolution so that a step stays within seconds on the host
-    scale = 1
-    while (w // scale) * (h // scale) > 640 * 368:
-        scale *= 2
-    dw, dh = max(16, (w // scale) // 16 * 16), max(16, (h // scale) // 16 * 16)
-    lit, t_light, t_frame = 0, 0.0, 0.0
+    # SAME config as the GPU arm: the draw runs at the config's full resolution, so both arms light the same visible set
+    # (a 1920x1080 draw + sync + lighting dispatch of config 2 takes ~0.2 s on 16 cores: W + K steps stay within seconds)
+    lit, t_light, t_frame, reqs = 0, 0.0, 0.0, 0
     for k in range(args.warmup + args.steps):
         e.reset_counters()
         t0 = time.perf_counter()
-        e.draw(dw, dh, aspect=h / w)
+        e.draw(w, h)
         e.sync(2, 1)
         t1 = time.perf_counter()
         e.update_lighting(1, 1000, frame_time(k))
@@ -243,20 +246,48 @@ def run_reference(args, scene, tiles, res, desc):
             lit += e.counters()["light"]["voxelsLit"]
             t_light += t2 - t1
             t_frame += t2 - t0
+            reqs += len(e.requests())
     value = lit / t_light if t_light > 0 else 0.0
-    cores = O.OracleEngine(map_size=(1, 1, 1), min_chunks=1).num_threads()
-    sample = "each step = %dx%d draw + sync + 1 lighting dispatch over the chunks that draw made visible" % (dw, dh)
+    K = max(args.steps, 1)
+    sample = "each step = %dx%d draw + sync + 1 lighting dispatch over the chunks that draw made visible (%d requests, %d voxels lit per step), %d OpenMP threads" % (w, h, reqs // K, lit // K, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * t_frame / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)"},
+        "ms_per_step": 1000.0 * t_frame / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "resolution": [w, h],
+                                         "requests_per_step": reqs / K, "voxels_lit_per_step": lit / K},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": lit / t_frame if t_frame > 0 else 0.0, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "glsl_baseline": gl_probe(),
     }), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def run_ours(args, scene, tiles, res, desc):
+def gl_probe():
+    """is there any OpenGL stack on this box the reference's GLSL path could run on?  (BASELINE.json: the GLSL baselines are reported
+    where the driver exposes EGL / OpenGL 4.3, otherwise named unavailable -- never fabricated)"""
+    found = []
+    try:
+        txt = subprocess.run(["ldconfig", "-p"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+        for line in txt.splitlines():
+            name = line.strip().split(" ")[0]
+            if any(name.startswith(k) for k in ("libEGL", "libOSMesa", "libGLX_nvidia", "libGL.so", "libglfw")):
+                found.append(name)
+    except Exception as ex:
+        return "unavailable (ldconfig failed: %r)" % (ex,)
+    dri = os.path.exists("/dev/dri")
+    have_loader = any(n.startswith(("libEGL.so", "libOSMesa", "libGL.so")) for n in found)
+    have_glfw = any(n.startswith("libglfw") for n in found)
+    if not have_loader:
+        return "unavailable (ldconfig -p lists no libEGL / libOSMesa / libGL loader%s; /dev/dri %s; no glslang / Mesa llvmpipe in the image, no network to install one)" % (
+            (", only " + ",".join(sorted(set(found)))) if found else "", "present" if dri else "absent")
+    return "unavailable (GL loader %s found but the reference needs GLFW + a GL 4.3 context%s; /dev/dri %s) -- not run" % (
+        ",".join(sorted(set(found))), "" if have_glfw else " and libglfw is absent", "present" if dri else "absent")
+
+
+def run_ours(args):
+    """process-wide set-up (device, NCCL, stream), then one measurement per config: the metric's config (default c2) as the JSON line's
+    top level, plus -- unless --no-c3 -- the full-size sparse 2048^3 map at 3840x2160 (config 3) as its "c3_4k" object, so that the
+    driver-run line carries both halves of BASELINE.json's metric at every N."""
     import torch
     import torch.distributed as dist
 
@@ -274,7 +305,6 @@ def run_ours(args, scene, tiles, res, desc):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    w, h = res
     L = dn.lib()
     dn.init(device=local)
     L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "auto": 2, "wave": 3}[args.light_kernel])
@@ -282,6 +312,32 @@ def run_ours(args, scene, tiles, res, desc):
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
     L.DN_b200_set_stream(stream.cuda_stream)
+    env = {"torch": torch, "dist": dist, "dn": dn, "L": L, "world": world, "rank": rank, "local": local, "device": device, "stream": stream}
+
+    out = measure_config(args, env, args.config, args.steps, args.warmup, want_cpu=not args.no_cpu_baseline)
+    if not args.no_c3 and args.config != "c3":
+        try:
+            c3 = measure_config(args, env, "c3", args.c3_steps, 3, want_cpu=False)
+            if rank == 0:
+                out["c3_4k"] = {"workload": c3["config"]["workload"], "steps": c3["steps"], "warmup": c3["warmup"], "frame_4k_ms": c3["ms_per_step"], "draw_4k_ms": c3["frame_ms"]["draw"],
+                                "c3_updates_per_s": c3["value"], "unit": UNIT, "frame_ms": c3["frame_ms"], "e2e": c3["e2e"], "roofline": c3["roofline"], "gpu_launches": c3["gpu_launches"],
+                                "light_kernel": c3["config"]["light_kernel"], "voxels_lit_per_step": c3["config"]["voxels_lit_per_step"], "requests_per_step": c3["config"]["requests_per_step"],
+                                "resident_chunks": c3["config"]["resident_chunks"], "build_s": c3["config"]["build_s"], "clocks": c3["clocks"]}
+        except Exception as ex:  # the metric's own config must still be reported
+            if rank == 0:
+                out["c3_4k"] = {"error": repr(ex)}
+    if rank == 0:
+        out["glsl_baseline"] = gl_probe()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_config(args, env, config, steps, warmup, want_cpu):
+    torch, dist, dn, L = env["torch"], env["dist"], env["dn"], env["L"]
+    world, rank, local, device, stream = env["world"], env["rank"], env["local"], env["device"], env["stream"]
+    scene, tiles, res, desc = CONFIGS[config]
+    w, h = res
 
     t_build = time.perf_counter()
     chunks = None
@@ -344,8 +400,8 @@ def run_ours(args, scene, tiles, res, desc):
 
     # config 4: the edits of every frame, generated before anything is timed
     edit_stream, edit_host_s = None, [0.0]
-    if args.config == "c4":
-        edit_stream = [frame_edits(k, tiles) for k in range(args.warmup + 2 * args.steps + 1)]
+    if config == "c4":
+        edit_stream = [frame_edits(k, tiles) for k in range(warmup + 2 * steps + 1)]
 
     host_s = {"edits": 0.0, "draw": 0.0, "read_back_enqueue": 0.0, "sync": 0.0, "light_compute": 0.0, "commit": 0.0, "wait_read": 0.0, "steps": 0}
 
@@ -444,17 +500,17 @@ def run_ours(args, scene, tiles, res, desc):
     if edit_stream is not None:
         edit_stream = edit_stream[PREROLL:]
     stats0 = e.stats()
-    for k in range(args.warmup):
+    for k in range(warmup):
         step(k, False, False)
     barrier()
 
     # ---- timed region 1: inputs resident, no read-back ----
     launches0 = int(L.DN_b200_kernel_launches())
-    phases, lit, reqs, clocks, wall = run_loop(args.warmup, args.steps, False)
+    phases, lit, reqs, clocks, wall = run_loop(warmup, steps, False)
     # ---- timed region 2: end to end through the API incl. framebuffer read-back into pinned host memory ----
     for key in host_s:
         host_s[key] = 0
-    phases2, lit2, reqs2, clocks2, wall2 = run_loop(args.warmup + args.steps, args.steps, True)
+    phases2, lit2, reqs2, clocks2, wall2 = run_loop(warmup + steps, steps, True)
     launches = int(L.DN_b200_kernel_launches()) - launches0  # this rank's kernels in both timed regions, counted by the library's launch wrappers
 
     def reduce_max(x):
@@ -466,7 +522,7 @@ def run_ours(args, scene, tiles, res, desc):
 
     phases = reduce_max(phases)
     phases2 = reduce_max(phases2)
-    K = max(args.steps, 1)
+    K = max(steps, 1)
     draw_ms, sync_ms, light_ms, commit_ms, rb_ms, frame_ms, light_total_ms, _ = (phases / K).tolist()
     frame2_ms = float(phases2[7] / K)
     light_total_s = phases[6] / 1000.0
@@ -484,7 +540,7 @@ def run_ours(args, scene, tiles, res, desc):
         sh.draw(fbs[0], view, proj)
     L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
     r_count = int(e.vol.contents.numLightingRequests)
-    sh.light_compute(1, 1000, frame_time(args.warmup + 2 * args.steps))
+    sh.light_compute(1, 1000, frame_time(warmup + 2 * steps))
     if rank == 0:
         cl = e.counters(reset=True)
     sh.light_exchange()
@@ -502,7 +558,7 @@ def run_ours(args, scene, tiles, res, desc):
         b_draw = algorithmic_bytes_draw(cd)
         st_ = e.stats()
         light_name = max((("dn_light_kernel", st_["lightLaunchesWarp"]), ("dn_light_flat_kernel", st_["lightLaunchesFlat"]), ("dn_wave_step_kernel", st_["lightLaunchesWave"])), key=lambda kv: kv[1])[0]
-        traffic = traffic_from_profile(light_name, args.config)
+        traffic = traffic_from_profile(light_name, config)
         roofline = {"kernel": light_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "traffic": traffic,
                     "algorithmic_bytes_per_launch": b_light, "compulsory_bytes_per_launch": b_compulsory,
@@ -513,9 +569,9 @@ def run_ours(args, scene, tiles, res, desc):
                     "note": "latency/divergence-bound gather traversal; the HBM fraction is expected to be small (SURVEY.md 8d)"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config in ("c3", "c5"):
+    if rank == 0 and world == 1 and want_cpu and config in ("c3", "c5"):
         cpu = {"skipped": "the oracle is a checker sized for seconds of work; its bounded sample is taken on the default config"}
-    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
+    elif rank == 0 and world == 1 and want_cpu:
         try:
             if chunks is None:
                 chunks, _ = make_chunks(scene, tiles)
@@ -527,7 +583,7 @@ def run_ours(args, scene, tiles, res, desc):
         stats = e.stats()
         edits = None
         if edit_stream is not None:
-            frames_run = args.warmup + 2 * args.steps + 1
+            frames_run = warmup + 2 * steps + 1
             edits = {"edits_per_step": EDITS_PER_FRAME, "host_apply_ms_per_step": 1000.0 * edit_host_s[0] / frames_run,
                      "chunks_uploaded_per_step": (stats["chunksUploaded"] - stats0["chunksUploaded"]) / frames_run,
                      "bytes_uploaded_per_step": (stats["bytesUploaded"] - stats0["bytesUploaded"]) / frames_run,
@@ -537,9 +593,9 @@ def run_ours(args, scene, tiles, res, desc):
         # per step: draw, compaction count + scan + write, lighting (1 kernel, or 2 per pass of the wavefront pair), commit, visible merge;
         # peer mode adds 2 barriers + the visible-bitmap merge, collective mode one OR kernel per rank and bitmap
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "parallelism": ("map replicated, request CTAs and 16-pixel rows interleaved x%d, exchange=%s" % (world, sh.exchange)) if world > 1 else "1 GPU",
+            "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "resolution": [w, h], "parallelism": ("map replicated, request CTAs and 16-pixel rows interleaved x%d, exchange=%s" % (world, sh.exchange)) if world > 1 else "1 GPU",
                        "light_kernel": {"mode": args.light_kernel, "dispatches_warp_per_request": int(stats["lightLaunchesWarp"]), "dispatches_persistent": int(stats["lightLaunchesFlat"]), "dispatches_wavefront": int(stats["lightLaunchesWave"]),
                                         "wavefront_passes_last": int(stats["lastWavePasses"]),
                                         "ns_per_4_requests": {"warp": stats["nsPerCtaWarp"], "persistent": stats["nsPerCtaFlat"], "wavefront": stats["nsPerCtaWave"]}}, "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
@@ -555,7 +611,8 @@ def run_ours(args, scene, tiles, res, desc):
         if edits:
             out["edits"] = edits
             out["e2e"]["h2d_bytes_per_step"] += int(edits["bytes_uploaded_per_step"])
-        print(json.dumps(out), flush=True)
+    else:
+        out = None
     if world > 1:
         ep, to = sh.barrier_status() if sh.exchange == "peer" else (0, 0)
         if to:
@@ -567,11 +624,13 @@ def run_ours(args, scene, tiles, res, desc):
         dist.barrier()
         if rank == 0:
             os.unlink(shm_path)
+        shm_map.close()
     for f in fbs:
         L.DN_b200_delete_framebuffer(f)
     e.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -582,6 +641,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the second timed block (full-size sparse 2048^3 map at 3840x2160, reported as \"c3_4k\")")
+    ap.add_argument("--c3-steps", type=int, default=8, help="timed frames of the c3_4k block (config 3 names 8 frames)")
     ap.add_argument("--light-kernel", default="auto", choices=["auto", "flat", "warp", "wave"], help="auto (default): the library times its three lighting kernels on live dispatches and runs the fastest one")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"], help="N > 1: kernels exchange over peer memory (default) or host-driven NCCL all-gathers")
     ap.add_argument("--sampler-ms", type=float, default=10.0, help="NVML clock sampling period during the timed region (0 = off)")
@@ -592,7 +653,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, scene, tiles, res, desc)
     else:
-        run_ours(args, scene, tiles, res, desc)
+        run_ours(args)
 
 
 if __name__ == "__main__":

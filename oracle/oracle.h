@@ -142,6 +142,7 @@ void     orb_get_voxel_position(const OrbBuffers* buf, uint32_t chunk, uint32_t 
 float    orb_rand(float seed);
 void     orb_rand_unit_sphere(float seed, float out[3]);
 int      orb_num_threads(void);
+void     orb_set_num_threads(int n); /* n <= 0: every online processor (ignores OMP_NUM_THREADS) */
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,17 @@ def have_ref():
     return os.path.exists(LIB_REF)
 
 
+def set_num_threads(n=0):
+    """OpenMP team size of every oracle dispatch in this process (one libgomp serves liboracle.so and libdoon_ref.so).
+    n <= 0: every online processor -- torchrun exports OMP_NUM_THREADS=1, which the reference arm of bench.py must not inherit."""
+    build()
+    L = C.CDLL(LIB_ORACLE)
+    L.orb_set_num_threads.argtypes = [C.c_int]
+    L.orb_num_threads.restype = C.c_int
+    L.orb_set_num_threads(int(n))
+    return int(L.orb_num_threads())
+
+
 def _view(ptr, dtype, count):
     if count == 0 or not ptr:
         return np.zeros(0, dtype=dtype)

@@ -1048,3 +1048,17 @@ int orb_num_threads(void)
 	return 1;
 #endif
 }
+
+/* bench.py --impl reference under torchrun inherits OMP_NUM_THREADS=1; the reference arm uses every host core it can,
+ * so the harness sets the team size itself.  n <= 0: all online processors. */
+void orb_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if(n <= 0)
+		n = omp_get_num_procs();
+	omp_set_dynamic(0);
+	omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}

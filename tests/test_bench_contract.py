@@ -11,12 +11,14 @@ import pytest
 from conftest import ROOT
 
 
-def _run(*args):
-    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+def _run(*args, env=None):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600,
+                          env=dict(os.environ, **(env or {})))
 
 
 def test_reference_arm_json_line():
-    p = _run("--impl", "reference", "--config", "small", "--steps", "2", "--warmup", "3")
+    # launched the way torch.distributed.run launches its workers: OMP_NUM_THREADS=1 must NOT throttle the reference arm
+    p = _run("--impl", "reference", "--config", "small", "--steps", "2", "--warmup", "3", env={"OMP_NUM_THREADS": "1"})
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -29,6 +31,17 @@ def test_reference_arm_json_line():
     e2e = d["e2e"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0 and 0 < e2e["value"] <= d["value"] and e2e["unit"] == d["unit"]
     assert "workload" in d["config"]
+    # same config as the GPU arm: the draw runs at the config's own resolution, on every host core
+    import bench
+    assert tuple(d["config"]["resolution"]) == bench.CONFIGS["small"][2]
+    assert "%dx%d draw" % bench.CONFIGS["small"][2] in cb["sample"]
+    assert cb["cores"] == os.cpu_count() or cb["cores"] == len(os.sched_getaffinity(0))
+    assert d["glsl_baseline"].startswith("unavailable (") or d["glsl_baseline"].startswith("available")
+
+
+def test_reference_arm_other_ranks_do_nothing():
+    p = _run("--impl", "reference", "--config", "small", "--gpus", "2", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert p.returncode == 0 and not p.stdout.strip()
 
 
 def test_gpu_arm_has_no_cpu_path():
