@@ -216,20 +216,24 @@ struct ScopedTimer
 /* sRGB -> linear, truncated, with the reference's constants and libm powf (voxel.c:1441-1447); host-only, no CUDA needed */
 static const uint8_t* albedo_lut()
 {
-	static uint8_t lut[256];
-	static bool ready = false;
-	if(!ready)
+	/* built once, by whichever thread gets here first: initialisation of a function-local static is synchronised (C++11), so the
+	 * pack workers -- up to 32 call this at once -- can never see a half-filled table */
+	struct Lut
 	{
-		for(int i = 0; i < 256; i++)
+		uint8_t v[256];
+		Lut()
 		{
-			float f = (float)i * 0.00392156862f;
-			f = powf(f, DN_GAMMA);
-			f = f * 255.0f;
-			lut[i] = (uint8_t)f;
+			for(int i = 0; i < 256; i++)
+			{
+				float f = (float)i * 0.00392156862f;
+				f = powf(f, DN_GAMMA);
+				f = f * 255.0f;
+				v[i] = (uint8_t)f;
+			}
 		}
-		ready = true;
-	}
-	return lut;
+	};
+	static const Lut lut;
+	return lut.v;
 }
 
 /* per material: does a voxel of it hide the faces it touches?  (voxel.c:1391-1394: a face is open when the neighbour is empty or
@@ -452,23 +456,14 @@ private:
 	bool quit = false;
 };
 
-/* ---- record-pool allocator: power-of-two nodes of 16..512 records, per-class free lists over a bump pointer ---- */
-static inline int node_class(uint32_t n)
-{
-	int c = 0;
-	uint32_t size = 16;
-	while(size < n) { size <<= 1; c++; }
-	return c;
-}
-
+/* ---- record-pool allocator: record_pool.h (a buddy system over 512-record blocks: split on acquire, merge on release) ---- */
 static void release_slot(VolumeImpl* v, uint32_t slot)
 {
 	const uint8_t cls = v->slotNodeClass[slot];
 	if(cls != 0xFF)
 	{
-		v->freeNodes[cls].push_back(v->slotNodeStart[slot]);
+		v->pool.release(v->slotNodeStart[slot], cls);
 		v->slotNodeClass[slot] = 0xFF;
-		v->pub.numVoxelNodes--;
 		v->stats.residentRecords -= v->slotNumVoxels[slot];
 		v->residentGroups -= (v->slotNumVoxels[slot] + 31) / 32;
 		v->slotNumVoxels[slot] = 0;
@@ -477,24 +472,13 @@ static void release_slot(VolumeImpl* v, uint32_t slot)
 
 static uint32_t acquire_node(VolumeImpl* v, uint32_t slot, uint32_t n)
 {
-	const int cls = node_class(n);
-	uint32_t start;
-	if(!v->freeNodes[cls].empty())
-	{
-		start = v->freeNodes[cls].back();
-		v->freeNodes[cls].pop_back();
-	}
-	else
-	{
-		start = (uint32_t)v->recordTop;
-		v->recordTop += (size_t)16 << cls;
-	}
+	const int cls = RecordPool::size_class(n);
+	const uint32_t start = v->pool.acquire(cls);
 	v->slotNodeStart[slot] = start;
 	v->slotNodeClass[slot] = (uint8_t)cls;
 	v->slotNumVoxels[slot] = n;
 	v->residentGroups += (n + 31) / 32;
 	v->stats.residentRecords += n;
-	v->pub.numVoxelNodes++;
 	return start;
 }
 
@@ -512,6 +496,7 @@ static uint32_t acquire_slot(VolumeImpl* v)
 		v->slotNodeStart.push_back(0);
 		v->slotNodeClass.push_back(0xFF);
 		v->slotNumVoxels.push_back(0);
+		v->slotTile.push_back(0);
 	}
 	return slot;
 }
@@ -618,6 +603,7 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 			v->tileSlotHost[tile] = slotPlus1;
 			v->stats.residentChunks++;
 		}
+		v->slotTile[slotPlus1 - 1] = tile;
 		hHeaders[i].voxelBase = acquire_node(v, slotPlus1 - 1, n);
 		for(int a = 0; a < 3; a++)
 		{
@@ -638,10 +624,10 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 		if(!device_reserve(v->slots, cap, true, true, "chunk slots"))
 			return false;
 	}
-	if(v->recordTop > v->records.cap)
+	if(v->pool.top > v->records.cap)
 	{
 		size_t cap = v->records.cap;
-		while(cap < v->recordTop) cap *= 2;
+		while(cap < v->pool.top) cap *= 2;
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing voxel buffer to accomodate %zu GPU voxels (%zu bytes)", cap, cap * sizeof(uint4));
 		if(!device_reserve(v->records, cap, true, true, "voxel records"))
 			return false;
@@ -682,6 +668,13 @@ static void sync_write(VolumeImpl* v)
 	if(v->touched.empty())
 		return;
 
+	if(vol->gpuVoxelLayout)
+	{
+		/* the pool is about to change: the snapshot made by DN_b200_mirror_voxel_layout is stale */
+		DN_FREE(vol->gpuVoxelLayout);
+		vol->gpuVoxelLayout = NULL;
+		vol->numVoxelNodes = 0;
+	}
 	ScopedTimer timer(&v->stats.lastUploadMs, c.uploadStream);
 	const double tScan0 = host_now_ms();
 	v->stats.lastPackHostMs = v->stats.lastEnqueueHostMs = 0.0f;
@@ -1540,9 +1533,9 @@ extern "C" bool DN_set_max_voxels_gpu(DNvolume* vol, size_t num)
 	VolumeImpl* v = impl_of(vol);
 	if(!device_ready(v, "DN_set_max_voxels_gpu"))
 		return false;
-	if(num < v->recordTop)
+	if(num < v->pool.top)
 	{
-		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_set_max_voxels_gpu: %zu records are in use, cannot shrink to %zu", v->recordTop, num);
+		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_set_max_voxels_gpu: %zu records are in use, cannot shrink to %zu", v->pool.top, num);
 		return false;
 	}
 	if(num <= v->records.cap)
@@ -1567,7 +1560,7 @@ static bool array_info(VolumeImpl* v, DNb200array which, void** ptr, size_t* byt
 	case DN_B200_TILE_SLOTS: *ptr = v->tileSlot.ptr; *bytes = tiles * sizeof(uint32_t); return true;
 	case DN_B200_VISIBLE:    *ptr = v->visible.ptr;  *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
 	case DN_B200_SLOTS:      *ptr = v->slots.ptr;    *bytes = (size_t)v->slotTop * sizeof(DnbSlot); return true;
-	case DN_B200_RECORDS:    *ptr = v->records.ptr;  *bytes = v->recordTop * sizeof(uint4); return true;
+	case DN_B200_RECORDS:    *ptr = v->records.ptr;  *bytes = v->pool.top * sizeof(uint4); return true;
 	case DN_B200_REQUESTS:   *ptr = v->requests.ptr; *bytes = v->requestsValid * sizeof(uint32_t); return true;
 	case DN_B200_PROPAGATE:  *ptr = v->propagate.ptr; *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
 	case DN_B200_STAGING:
@@ -1671,6 +1664,11 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 	v->stats.lightLaunchesFlat = v->tuner.launches[1];
 	v->stats.nsPerCtaWarp = (float)v->tuner.nsPerCta[0];
 	v->stats.nsPerCtaFlat = (float)v->tuner.nsPerCta[1];
+	v->stats.usedNodes = v->pool.usedNodes;
+	v->stats.freeNodes = v->pool.freeNodeCount;
+	v->stats.recordTop = v->pool.top;
+	v->stats.nodeSplits = v->pool.splits;
+	v->stats.nodeMerges = v->pool.merges;
 	v->stats.lightLaunchesWave = v->tuner.launches[2];
 	v->stats.nsPerCtaWave = (float)v->tuner.nsPerCta[2];
 	v->stats.lastWavePasses = v->tuner.lastWavePasses;
@@ -1681,6 +1679,47 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 			v->stats.voxelsLit = lit;
 	}
 	*out = v->stats;
+}
+
+/* snapshot of the record-pool allocator in the reference's public form (voxel.h:74-79,108-117; DoonEngine/b200.h) */
+extern "C" bool DN_b200_mirror_voxel_layout(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	DN_FREE(vol->gpuVoxelLayout);
+	vol->gpuVoxelLayout = NULL;
+	vol->numVoxelNodes = 0;
+	const size_t count = v->pool.usedNodes + v->pool.freeNodeCount;
+	DNvoxelNode* nodes = (DNvoxelNode*)DN_MALLOC(sizeof(DNvoxelNode) * (count ? count : 1));
+	if(!nodes)
+	{
+		report(DN_MESSAGE_CPU_MEMORY, DN_MESSAGE_ERROR, "failed to allocate %zu voxel nodes", count);
+		return false;
+	}
+	size_t n = 0;
+	for(uint32_t slot = 0; slot < v->slotTop; slot++)
+	{
+		if(v->slotNodeClass[slot] == 0xFF)
+			continue;
+		const uint32_t tile = v->slotTile[slot];
+		nodes[n].size = 16u << v->slotNodeClass[slot];
+		nodes[n].startPos = v->slotNodeStart[slot];
+		nodes[n].chunkPos.x = (int)(tile % vol->mapSize.x);
+		nodes[n].chunkPos.y = (int)((tile / vol->mapSize.x) % vol->mapSize.y);
+		nodes[n].chunkPos.z = (int)(tile / ((size_t)vol->mapSize.x * vol->mapSize.y));
+		n++;
+	}
+	for(size_t at = 0; at < v->pool.nodeFree.size(); at++)
+		if(v->pool.nodeFree[at] != 0xFF)
+		{
+			nodes[n].size = 16u << v->pool.nodeFree[at];
+			nodes[n].startPos = at << 4;
+			nodes[n].chunkPos.x = nodes[n].chunkPos.y = nodes[n].chunkPos.z = -1;
+			n++;
+		}
+	std::sort(nodes, nodes + n, [](const DNvoxelNode& a, const DNvoxelNode& b) { return a.startPos < b.startPos; });
+	vol->gpuVoxelLayout = nodes;
+	vol->numVoxelNodes = n;
+	return n == count;
 }
 
 extern "C" cudaError_t dnb_launch_or_bits(uint32_t* dst, const uint32_t* src, uint32_t words, cudaStream_t stream);
@@ -1877,10 +1916,29 @@ extern "C" size_t DN_b200_step_map_batch(DNvolume* vol, size_t count, const DNve
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_step_map_batch: at most 2^31 - 1 rays per call");
 		return 0;
 	}
-	/* DN_step_map sees every edit at once (it reads the CPU map); so must this: pending edits are uploaded first.  A replica of a
-	 * peer-attached volume cannot do that on its own (the upload is fenced against the other replicas): its caller syncs. */
-	if(!v->touched.empty() && !v->peerAttached)
-		sync_write(v);
+	/* DN_step_map sees every edit at once (it reads the CPU map); this call walks the DEVICE map, which is as of the last writing
+	 * sync.  It does not upload pending edits behind the caller's back: that would consume the chunks' `updated` flags outside the
+	 * DN_sync_gpu protocol, and a later DN_sync_gpu(READ*, lightingSplit > 1) would no longer force-light the edited chunks
+	 * (voxel.c:1470) -- the lighting schedule would differ from a run that picked with DN_step_map.  So: refuse, and say what to do. */
+	if(!v->touched.empty())
+	{
+		bool pending = false;
+		for(uint32_t tile : v->touched)
+		{
+			const bool onCpu = vol->map[tile].flag != 0;
+			const bool onGpu = v->tileSlotHost[tile] != 0;
+			if((onCpu && (!onGpu || vol->chunks[vol->map[tile].chunkIndex].updated)) || (!onCpu && onGpu))
+			{
+				pending = true;
+				break;
+			}
+		}
+		if(pending)
+		{
+			report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_b200_step_map_batch: the map has edits that are not on the device yet; call DN_sync_gpu(vol, DN_WRITE or DN_READ_WRITE, split) first (or use DN_step_map, which reads the CPU map)");
+			return 0;
+		}
+	}
 
 	cudaStream_t s = ctx().stream();
 	if(!device_reserve(v->pickRays, count * 6, false, false, "picking rays") || !device_reserve(v->pickHits, count, false, false, "picking results"))
@@ -1976,10 +2034,10 @@ extern "C" bool DN_b200_save_lighting(DNvolume* vol, const char* filePath)
 	if(!device_ready(v, "DN_b200_save_lighting") || !DN_b200_synchronize())
 		return false;
 	std::vector<DnbSlot> slots(v->slotTop);
-	std::vector<uint4> records(v->recordTop);
+	std::vector<uint4> records(v->pool.top);
 	std::vector<uint32_t> visible((num_tiles(vol) + 31) / 32);
 	if((v->slotTop && !cuda_ok(cudaMemcpy(slots.data(), v->slots.ptr, slots.size() * sizeof(DnbSlot), cudaMemcpyDeviceToHost), "slot download")) ||
-	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")) ||
+	   (v->pool.top && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")) ||
 	   (!visible.empty() && !cuda_ok(cudaMemcpy(visible.data(), v->visible.ptr, visible.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost), "visible bitmap download")))
 		return false;
 	FILE* f = fopen(filePath, "wb");
@@ -2033,10 +2091,10 @@ extern "C" int DN_b200_load_lighting(DNvolume* vol, const char* filePath)
 		return -1;
 	}
 	std::vector<DnbSlot> slots(v->slotTop);
-	std::vector<uint4> records(v->recordTop);
+	std::vector<uint4> records(v->pool.top);
 	std::vector<uint32_t> visible((num_tiles(vol) + 31) / 32);
 	if((v->slotTop && !cuda_ok(cudaMemcpy(slots.data(), v->slots.ptr, slots.size() * sizeof(DnbSlot), cudaMemcpyDeviceToHost), "slot download")) ||
-	   (v->recordTop && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")) ||
+	   (v->pool.top && !cuda_ok(cudaMemcpy(records.data(), v->records.ptr, records.size() * sizeof(uint4), cudaMemcpyDeviceToHost), "record download")) ||
 	   (!visible.empty() && !cuda_ok(cudaMemcpy(visible.data(), v->visible.ptr, visible.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost), "visible bitmap download")))
 	{
 		fclose(f);
@@ -2077,7 +2135,7 @@ extern "C" int DN_b200_load_lighting(DNvolume* vol, const char* filePath)
 	if(!visible.empty() && !cuda_ok(cudaMemcpy(v->visible.ptr, visible.data(), visible.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "visible bitmap upload"))
 		return -1;
 	if((v->slotTop && !cuda_ok(cudaMemcpy(v->slots.ptr, slots.data(), slots.size() * sizeof(DnbSlot), cudaMemcpyHostToDevice), "slot upload")) ||
-	   (v->recordTop && !cuda_ok(cudaMemcpy(v->records.ptr, records.data(), records.size() * sizeof(uint4), cudaMemcpyHostToDevice), "record upload")))
+	   (v->pool.top && !cuda_ok(cudaMemcpy(v->records.ptr, records.data(), records.size() * sizeof(uint4), cudaMemcpyHostToDevice), "record upload")))
 		return -1;
 	return restored;
 }

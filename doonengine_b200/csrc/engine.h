@@ -5,6 +5,7 @@
 #include "DoonEngine/b200.h"
 #include "DoonEngine/voxel.h"
 #include "kernels.h"
+#include "record_pool.h"
 
 #include <cuda_runtime.h>
 #include <vector>
@@ -12,8 +13,6 @@
 namespace dnb
 {
 
-/* size classes of the record pool: 16, 32, 64, 128, 256, 512 records (same node sizes as voxel.c:1557-1559) */
-enum { NUM_NODE_CLASSES = 6 };
 
 template <typename T> struct DeviceArray
 {
@@ -65,8 +64,8 @@ struct VolumeImpl
 	std::vector<uint32_t> slotNodeStart;  /* per slot: first record of its node */
 	std::vector<uint8_t>  slotNodeClass;  /* per slot: size class of its node, 0xFF = none */
 	std::vector<uint32_t> slotNumVoxels;  /* per slot: records in use */
-	std::vector<uint32_t> freeNodes[NUM_NODE_CLASSES];
-	size_t                recordTop = 0;  /* bump pointer of the record pool */
+	RecordPool            pool;           /* the record-pool allocator (record_pool.h) */
+	std::vector<uint32_t> slotTile;       /* per slot: owner tile (for the gpuVoxelLayout mirror) */
 	size_t                residentGroups = 0; /* sum over resident chunks of ceil(records/32): upper bound of the request count */
 
 	/* ---- edit tracking ---- */

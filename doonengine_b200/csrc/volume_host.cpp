@@ -251,27 +251,38 @@ uint16_t encode_chunk(const DNchunk* chunk, DNvolume* vol, uint8_t* out)
 	return (uint16_t)(p - out);
 }
 
-/* voxel.c:433-518 */
-void decode_chunk(const uint8_t* in, DNvolume* vol, DNchunk* chunk)
+/* voxel.c:433-518, with an end pointer: a malformed or truncated stream stops the decode (false) instead of reading past the
+ * record (the reference trusts the file: voxel.c:547-553 reads a file-supplied size into a fixed buffer and walks it unchecked) */
+bool decode_chunk(const uint8_t* in, const uint8_t* end, DNvolume* vol, DNchunk* chunk)
 {
-	memcpy(&chunk->pos, in, sizeof(DNivec3));
-	in += sizeof(DNivec3);
 	chunk->updated = false;
 	chunk->numVoxels = 0;
 	chunk->numVoxelsGpu = 0;
+	if((size_t)(end - in) < sizeof(DNivec3))
+	{
+		chunk->pos = {-1, -1, -1};
+		return false;
+	}
+	memcpy(&chunk->pos, in, sizeof(DNivec3));
+	in += sizeof(DNivec3);
 	if(!DN_in_map_bounds(vol, chunk->pos))
-		return;
+		return true;
 
+#define NEED(n) do { if((size_t)(end - in) < (size_t)(n)) return false; } while(0)
+	NEED(1);
 	const uint8_t numNormal = *in++;
 	const uint8_t* normalPal = in;
+	NEED(3 * (size_t)numNormal + 1);
 	in += 3 * (size_t)numNormal;
 	const uint8_t numAlbedo = *in++;
 	const uint8_t* albedoPal = in;
+	NEED(3 * (size_t)numAlbedo);
 	in += 3 * (size_t)numAlbedo;
 
 	int done = 0;
 	while(done < DN_CHUNK_LENGTH)
 	{
+		NEED(2);
 		const uint8_t material = *in++;
 		const uint8_t num = *in++;
 		for(int i = done; i < done + num && i < DN_CHUNK_LENGTH; i++)
@@ -284,19 +295,35 @@ void decode_chunk(const uint8_t* in, DNvolume* vol, DNchunk* chunk)
 				continue;
 			}
 			const uint8_t* n;
-			if(numNormal > 0) n = normalPal + 3 * (size_t)(*in++);
-			else { n = in; in += 3; }
+			if(numNormal > 0)
+			{
+				NEED(1);
+				const uint8_t k = *in++;
+				if(k >= numNormal)
+					return false; /* palette index past the palette */
+				n = normalPal + 3 * (size_t)k;
+			}
+			else { NEED(3); n = in; in += 3; }
 			const uint8_t* a;
-			if(numAlbedo > 0) a = albedoPal + 3 * (size_t)(*in++);
-			else { a = in; in += 3; }
+			if(numAlbedo > 0)
+			{
+				NEED(1);
+				const uint8_t k = *in++;
+				if(k >= numAlbedo)
+					return false;
+				a = albedoPal + 3 * (size_t)k;
+			}
+			else { NEED(3); a = in; in += 3; }
 			vx.normal = ((uint32_t)material << 24) | ((uint32_t)n[0] << 16) | ((uint32_t)n[1] << 8) | n[2];
 			vx.albedo = ((uint32_t)a[0] << 24) | ((uint32_t)a[1] << 16) | ((uint32_t)a[2] << 8);
 			chunk->numVoxels++;
 		}
 		if(num == 0)
-			break; /* malformed stream: a zero-length run would never terminate */
+			return false; /* malformed stream: a zero-length run would never terminate */
 		done += num;
 	}
+#undef NEED
+	return true;
 }
 
 } // namespace
@@ -318,6 +345,26 @@ extern "C" DNvolume* DN_load_volume(const char* filePath, unsigned int minChunks
 		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "file \"%s\" is truncated", filePath);
 		return NULL;
 	}
+	/* the header is untrusted: every chunk record takes at least 2 bytes of the file, and the map must be addressable by a
+	 * 28-bit tile index (voxelLighting.comp:9) -- refuse before allocating anything from these numbers */
+	long fileBytes = -1;
+	{
+		const long here = ftell(f);
+		if(here >= 0 && fseek(f, 0, SEEK_END) == 0)
+		{
+			fileBytes = ftell(f);
+			fseek(f, here, SEEK_SET);
+		}
+	}
+	const unsigned long long tiles = (unsigned long long)mapSize.x * mapSize.y * mapSize.z;
+	if(mapSize.x == 0 || mapSize.y == 0 || mapSize.z == 0 || mapSize.x > (1u << 20) || mapSize.y > (1u << 20) || mapSize.z > (1u << 20) || tiles > (1ull << 28) ||
+	   (fileBytes >= 0 && chunkCap > (uint64_t)fileBytes / 2))
+	{
+		fclose(f);
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "file \"%s\" has an implausible header (map %ux%ux%u, %llu chunk records, %ld bytes)", filePath, mapSize.x, mapSize.y, mapSize.z,
+		       (unsigned long long)chunkCap, fileBytes);
+		return NULL;
+	}
 	DNvolume* vol = DN_create_volume(mapSize, minChunks);
 	if(!vol || !DN_set_max_chunks(vol, (size_t)chunkCap))
 	{
@@ -328,15 +375,22 @@ extern "C" DNvolume* DN_load_volume(const char* filePath, unsigned int minChunks
 	}
 	VolumeImpl* v = impl_of(vol);
 
-	std::vector<uint8_t> buf(sizeof(DNchunk) * 2);
-	bool ok = true;
+	std::vector<uint8_t> buf(UINT16_MAX); /* a record's size field is 16 bits: whatever the file says fits */
+	bool ok = true, malformed = false;
 	for(size_t i = 0; i < (size_t)chunkCap && ok; i++)
 	{
 		uint16_t size;
 		ok = fread(&size, sizeof(uint16_t), 1, f) == 1 && fread(buf.data(), 1, size, f) == size;
 		if(!ok)
 			break;
-		decode_chunk(buf.data(), vol, &vol->chunks[i]);
+		if(!decode_chunk(buf.data(), buf.data() + size, vol, &vol->chunks[i]))
+		{
+			/* a damaged record: drop the chunk rather than keep half of it */
+			malformed = true;
+			vol->chunks[i].pos = {-1, -1, -1};
+			vol->chunks[i].numVoxels = 0;
+			continue;
+		}
 		if(DN_in_map_bounds(vol, vol->chunks[i].pos))
 		{
 			const size_t mapIndex = DN_FLATTEN_INDEX(vol->chunks[i].pos, mapSize);
@@ -345,6 +399,8 @@ extern "C" DNvolume* DN_load_volume(const char* filePath, unsigned int minChunks
 			touch_tile(v, mapIndex);
 		}
 	}
+	if(malformed)
+		report(DN_MESSAGE_FILE_IO, DN_MESSAGE_ERROR, "file \"%s\" holds malformed chunk records; those chunks were dropped", filePath);
 
 	ok = ok && fread(vol->materials, sizeof(DNmaterial), DN_MAX_MATERIALS, f) == DN_MAX_MATERIALS;
 	ok = ok && fread(&vol->camPos, sizeof(DNvec3), 1, f) == 1 && fread(&vol->camOrient, sizeof(DNvec3), 1, f) == 1;
@@ -536,10 +592,13 @@ extern "C" bool DN_set_map_size(DNvolume* vol, DNuvec3 size)
 	v->slotNodeStart.clear();
 	v->slotNodeClass.clear();
 	v->slotNumVoxels.clear();
-	for(int c = 0; c < NUM_NODE_CLASSES; c++)
-		v->freeNodes[c].clear();
-	v->recordTop = 0;
+	v->pool.clear();
+	v->slotTile.clear();
 	v->residentGroups = 0;
+	v->stats.residentChunks = 0;
+	v->stats.residentRecords = 0;
+	DN_FREE(vol->gpuVoxelLayout);
+	vol->gpuVoxelLayout = NULL;
 	for(int a = 0; a < 3; a++)
 	{
 		v->occMin[a] = 0x3FFFFFFF;

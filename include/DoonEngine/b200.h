@@ -99,10 +99,22 @@ typedef struct DNb200stats
 	uint64_t lightLaunchesWave;                             /* lighting dispatches run by the wavefront kernels */
 	float    nsPerCtaWave;                                  /* auto mode: their time per 4 requests */
 	uint32_t lastWavePasses;                                /* serve + step passes the last wavefront dispatch queued */
+	uint32_t pad0;
+	uint64_t nodeSplits, nodeMerges;                        /* record-pool allocator: buddy splits / merges since creation */
+	uint64_t usedNodes, freeNodes;                          /* record-pool nodes now */
+	uint64_t recordTop;                                     /* records of the pool handed out to the allocator (multiple of 512) */
 } DNb200stats;
 void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
 void DN_b200_enable_timing(bool enable);
 uint64_t DN_b200_kernel_launches(void); /* CUDA kernels this library has launched since it was loaded (all volumes) */ /* record CUDA events around each kernel group (adds a sync when read) */
+
+/* vol->gpuVoxelLayout / vol->numVoxelNodes (voxel.h:108-117): upstream this array IS the allocator (O(nodes) scans per upload,
+ * voxel.c:1560-1592).  Here the allocator is a buddy system keyed by address (csrc/engine.cpp), so the public array is only a
+ * MIRROR, built when asked for: after this call gpuVoxelLayout holds every node of the record pool -- used ones with their owner's
+ * chunkPos, free ones with chunkPos.x = -1 -- in ascending startPos order, and numVoxelNodes their count.  The next call that changes
+ * the pool (a writing DN_sync_gpu with pending edits, DN_set_map_size) frees the mirror again and resets numVoxelNodes to 0; between
+ * mirrors the two fields are NULL and 0, never a count without an array.  Returns false on allocation failure. */
+bool DN_b200_mirror_voxel_layout(DNvolume* vol);
 
 /* tiles whose host-side state was changed WITHOUT going through a DN_* call (e.g. writing vol->chunks[i].voxels
  * directly and setting .updated) must be announced, because DN_sync_gpu does not scan the whole map */
@@ -124,8 +136,10 @@ size_t DN_b200_set_chunks(DNvolume* vol, size_t count, const DNivec3* mapPositio
 /* ---- batched picking: DN_step_map (voxel.c:1195-1272) for `count` rays in one call, walked on the DEVICE map (csrc/pick.cu: the
  * reference's single-axis voxel DDA over the occupancy bit-grid and the chunks' surface masks).  Per ray the outputs are exactly
  * what DN_step_map would return: hitFlags[i] = its return value; hitNormals[i] is always written (-1000 if no step was taken);
- * hitPositions[i] / hitVoxels[i] only on a hit.  Any output array may be NULL.  Pending edits are uploaded first (a writing sync),
- * except on a peer-attached replica, whose caller must DN_sync_gpu(DN_WRITE) itself.  Returns the number of hits. ---- */
+ * hitPositions[i] / hitVoxels[i] only on a hit.  Any output array may be NULL.  The device map is as of the last writing DN_sync_gpu:
+ * with edits pending the call reports an error and returns 0 without touching the outputs (it never syncs behind the caller's back --
+ * that would consume the chunks' `updated` flags outside the DN_sync_gpu protocol and change which chunks a lightingSplit > 1 schedule
+ * force-lights, voxel.c:1470).  Returns the number of hits. ---- */
 size_t DN_b200_step_map_batch(DNvolume* vol, size_t count, const DNvec3* rayDirs, const DNvec3* rayPositions, int maxSteps, DNivec3* hitPositions, DNvoxel* hitVoxels,
                               DNivec3* hitNormals, uint8_t* hitFlags);
 

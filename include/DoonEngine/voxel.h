@@ -10,7 +10,8 @@
  *     DN_b200_create_framebuffer() (DoonEngine/b200.h), a linear RGBA32F image in device memory.
  *   - the map is RESIDENT: every chunk the CPU map holds is uploaded by DN_sync_gpu(DN_WRITE / DN_READ_WRITE);
  *     there is no demand streaming / LRU eviction (reference voxel.c:1554-1640), so `minChunks` only sizes
- *     the initial pools.  `gpuVoxelLayout`/`numVoxelNodes` mirror this library's own record allocator.
+ *     the initial pools.  `gpuVoxelLayout` / `numVoxelNodes` are NULL / 0 except right after
+ *     DN_b200_mirror_voxel_layout() (DoonEngine/b200.h), which builds a snapshot of this library's own record allocator.
  *   - `lightingRequests` is mirrored to the host lazily (DN_b200_fetch_lighting_requests); the request list
  *     is built on the device.  `numLightingRequests` is valid after every DN_sync_gpu that reads.
  *   - raster composition (rasterColorTexture/rasterDepthTexture >= 0) and cubemap skies are not implemented:

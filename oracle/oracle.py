@@ -447,6 +447,26 @@ class RefEngine(_EngineBase):
     def update_lighting(self, num_diffuse=1, max_diffuse=1000, time=1.0):
         self.L.DN_update_lighting(self.vol, num_diffuse, max_diffuse, C.c_float(time))
 
+    def step_map(self, direction, origin, max_steps):
+        """the reference's OWN DN_step_map (voxel.c:1195-1272) on its CPU map: (hit, cell, face normal, (material, normal xyz, albedo rgb))"""
+        if not hasattr(self, "_step_types"):
+            class V3(C.Structure):
+                _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+            class Col(C.Structure):
+                _fields_ = [("r", C.c_uint8), ("g", C.c_uint8), ("b", C.c_uint8)]
+
+            class Vox(C.Structure):
+                _fields_ = [("material", C.c_uint8), ("normal", V3), ("albedo", Col)]
+
+            self._step_types = (V3, Vox)
+            self.L.DN_step_map.restype = C.c_bool
+            self.L.DN_step_map.argtypes = [C.POINTER(DNvolume), V3, V3, C.c_uint, C.POINTER(self.DNivec3), C.POINTER(Vox), C.POINTER(self.DNivec3)]
+        V3, Vox = self._step_types
+        hp, hn, hv = self.DNivec3(), self.DNivec3(), Vox()
+        ok = bool(self.L.DN_step_map(self.vol, V3(*[float(x) for x in direction]), V3(*[float(x) for x in origin]), int(max_steps), C.byref(hp), C.byref(hv), C.byref(hn)))
+        return ok, (hp.x, hp.y, hp.z), (hn.x, hn.y, hn.z), (hv.material, (hv.normal.x, hv.normal.y, hv.normal.z), (hv.albedo.r, hv.albedo.g, hv.albedo.b))
+
     def uniforms(self, program):
         u = OrbUniforms()
         self.L.fgl_collect_uniforms(program, C.byref(u))

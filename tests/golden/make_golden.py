@@ -13,6 +13,9 @@ restatement of its shaders (oracle/shader_cpu.c) -- see oracle/oracle.h for the 
                        request list of every frame, and the packed voxel records after 1 and after 4 lit frames
   mixed_frames.npz   the same for doonengine_b200.scenes.mixed_materials (all material kinds incl. glass)
   codec_kat.npz      DN_compress_voxel / DN_decompress_voxel known answers and the albedo linearisation table
+  picks.npz          the reference's own DN_step_map (voxel.c:1195-1272) on 3 000 rays over the demo map and 3 000 over a terrain
+                     map: hit flag, hit cell, face normal, voxel (the chain from DN_b200_step_map_batch / this library's DN_step_map
+                     to the reference)
 """
 import ctypes as C
 import filecmp
@@ -77,8 +80,61 @@ def run_protocol(engine, out, prefix=""):
     out[prefix + "image_final"] = engine.draw(W, H)
 
 
+def pick_rays(rng, n, tiles):
+    """origins in and around the map (chunk units), random directions incl. axis-parallel ones, zero components, origins on cell faces"""
+    t = np.array(tiles, np.float32)
+    o = (rng.random((n, 3), dtype=np.float32) * (t + 2.0) - 1.0).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    k = n // 10
+    d[:k] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice(np.array([-1.0, 1.0], np.float32), (k, 1))
+    d[k:2 * k, rng.integers(0, 3)] = 0.0
+    o[2 * k:3 * k] = np.floor(o[2 * k:3 * k] * 8.0) / 8.0
+    return d, o
+
+
+def run_picks(ref, d, o, steps, out, prefix):
+    n = d.shape[0]
+    hit = np.zeros(n, np.uint8)
+    pos = np.zeros((n, 3), np.int32)
+    normal = np.zeros((n, 3), np.int32)
+    material = np.zeros(n, np.uint8)
+    albedo = np.zeros((n, 3), np.uint8)
+    vnormal = np.zeros((n, 3), np.float32)
+    for i in range(n):
+        ok, p, nrm, vox = ref.step_map(d[i], o[i], steps)
+        hit[i] = ok
+        normal[i] = nrm
+        if ok:
+            pos[i] = p
+            material[i], vnormal[i], albedo[i] = vox[0], vox[1], vox[2]
+    out.update({prefix + "_dirs": d, prefix + "_origins": o, prefix + "_steps": np.int32(steps), prefix + "_hit": hit, prefix + "_pos": pos, prefix + "_normal": normal,
+                prefix + "_material": material, prefix + "_albedo": albedo, prefix + "_vnormal": vnormal})
+    return int(hit.sum())
+
+
+def make_picks():
+    rng = np.random.default_rng(2026)
+    out = {}
+    ref = O.RefEngine(voxvol=REF_DEMO, min_chunks=256)
+    d, o = pick_rays(rng, 3000, ref.map_size)
+    n1 = run_picks(ref, d, o, 400, out, "demo")
+    ref.close()
+    tiles = (8, 8, 8)
+    ref = O.RefEngine(map_size=tiles, min_chunks=600)
+    scenes.build(ref, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+    d, o = pick_rays(rng, 3000, tiles)
+    o[:, 1] *= 0.6  # more origins below the surface (inside solid, incl. culled interior voxels)
+    n2 = run_picks(ref, d, o, 300, out, "terrain")
+    out["terrain_tiles"] = np.array(tiles, np.int32)
+    ref.close()
+    np.savez_compressed(os.path.join(HERE, "picks.npz"), **out)
+    print("picks: %d + %d hits of 3000 + 3000 rays" % (n1, n2))
+
+
 def main():
     O.build()
+    make_picks()
     # --- demo.voxvol through the reference's own load + save ---
     ref = O.RefEngine(voxvol=REF_DEMO, min_chunks=256)
     ref.L.DN_save_volume.restype = C.c_bool

@@ -278,3 +278,33 @@ def test_bulk_chunks_equal_single_chunks(dn):
             assert pa[0].tobytes() == pb[0].tobytes() and np.array_equal(pa[1], pb[1])
     a.close()
     b.close()
+
+
+def _check_picks(e, g, name):
+    hit = g[name + "_hit"].astype(bool)
+    steps = int(g[name + "_steps"])
+    for i, (d, o) in enumerate(zip(g[name + "_dirs"], g[name + "_origins"])):
+        ok, pos, nrm, vox = e.step_map(d, o, steps)
+        assert ok == bool(hit[i]), "%s ray %d: hit flag" % (name, i)
+        assert nrm == tuple(int(x) for x in g[name + "_normal"][i]), "%s ray %d: normal" % (name, i)
+        if ok:
+            assert pos == tuple(int(x) for x in g[name + "_pos"][i]), "%s ray %d: cell" % (name, i)
+            assert vox.material == int(g[name + "_material"][i]) and (vox.albedo.r, vox.albedo.g, vox.albedo.b) == tuple(int(x) for x in g[name + "_albedo"][i])
+            assert np.array_equal(np.array([vox.normal.x, vox.normal.y, vox.normal.z], np.float32).view(np.uint32), g[name + "_vnormal"][i].view(np.uint32))
+    return int(hit.sum())
+
+
+def test_step_map_against_reference_goldens(dn):
+    """this library's DN_step_map (host map) returns, ray by ray, what the REFERENCE's own DN_step_map returned for the 6 000 rays of
+    tests/golden/picks.npz (voxel.c:1195-1272 compiled in place; make_golden.py).  The GPU suite checks DN_b200_step_map_batch
+    against the same file, so both picking paths are chained to the reference, not to each other."""
+    from doonengine_b200 import scenes
+    g = np.load(os.path.join(GOLDEN, "picks.npz"))
+    e = dn.Engine(voxvol=DEMO, min_chunks=256, host_only=True)
+    assert _check_picks(e, g, "demo") > 1000
+    e.close()
+    tiles = tuple(int(x) for x in g["terrain_tiles"])
+    e = dn.Engine(map_size=tiles, min_chunks=600, host_only=True)
+    scenes.build(e, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+    assert _check_picks(e, g, "terrain") > 1000
+    e.close()

@@ -82,3 +82,45 @@ def test_edit_stream_with_lighting_split(engines):
         _same_state(r, o, "frame %d" % k)
     r.close()
     o.close()
+
+
+def test_step_map_equals_reference_live(engines, dn):
+    """DN_step_map of libdoon_b200.so against the reference's own (oracle/_ref) on fresh rays: 6 000 over a sparse-ball map incl.
+    rays after 500 random edits (sets and removals) applied to both maps -- hit flag, cell, face normal, voxel contents."""
+    from doonengine_b200 import scenes
+    O = engines
+    tiles = (6, 6, 6)
+    r = O.RefEngine(map_size=tiles, min_chunks=256)
+    e = dn.Engine(map_size=tiles, min_chunks=256, host_only=True)
+    for eng in (r, e):
+        scenes.build(eng, scenes.sparse_balls(tiles), **scenes.sparse_camera(tiles))
+    rng = np.random.default_rng(99)
+
+    def compare(n, steps, what):
+        t = np.array(tiles, np.float32)
+        o = (rng.random((n, 3), dtype=np.float32) * (t + 2.0) - 1.0).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        d[: n // 20] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, n // 20)]
+        hits = 0
+        for i in range(n):
+            ok_r, pos_r, nrm_r, vox_r = r.step_map(d[i], o[i], steps)
+            ok_e, pos_e, nrm_e, vox_e = e.step_map(d[i], o[i], steps)
+            assert ok_r == ok_e and nrm_r == nrm_e, "%s ray %d" % (what, i)
+            if ok_r:
+                hits += 1
+                assert pos_r == pos_e, "%s ray %d" % (what, i)
+                assert vox_r == (vox_e.material, (vox_e.normal.x, vox_e.normal.y, vox_e.normal.z), (vox_e.albedo.r, vox_e.albedo.g, vox_e.albedo.b)), "%s ray %d" % (what, i)
+        return hits
+
+    assert compare(3000, 400, "sparse") > 300
+    for _ in range(500):
+        p = rng.integers(0, 48, 3)
+        mp, cp = tuple(int(x) // 8 for x in p), tuple(int(x) % 8 for x in p)
+        nw, aw = (0xFF000000, 0) if rng.random() < 0.4 else (0x007FFF7F | (int(rng.integers(0, 4)) << 24), 0x80402000)
+        for eng in (r, e):
+            eng.set_voxel(mp, cp, nw, aw)
+    assert compare(3000, 400, "sparse after edits") > 300
+    assert compare(300, 5, "sparse, 5 steps") >= 0
+    r.close()
+    e.close()

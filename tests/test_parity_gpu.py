@@ -577,6 +577,177 @@ def test_batched_picking_equals_step_map(dn, light_kernel):
     assert check(e, d, o, 300, "terrain") > 1000
     pos = rng.integers(0, 64, (400, 3)).astype(np.int32)
     vox = np.stack([np.where(rng.random(400) < 0.5, 0xFFFFFFFF, 0x007FFF7F), np.full(400, 0x80402000)], axis=1).astype(np.uint32)
-    e.set_voxels(pos, vox)  # NOT synced: the batch call uploads pending edits itself
+    e.set_voxels(pos, vox)
+    # NOT synced: the device map is stale, and the call must say so instead of syncing behind the caller's back
+    # (that would eat the `updated` flags a lightingSplit > 1 schedule relies on, voxel.c:1470)
+    dn.messages(clear=True)
+    stale = e.step_map_batch(d[:16], o[:16], 300)
+    assert int(stale["hit"].sum()) == 0 and any("not on the device yet" in m[2] for m in dn.messages())
+    upd = [int(t) for t in np.unique(pos[:, 0] // 8 + 8 * (pos[:, 1] // 8 + 8 * (pos[:, 2] // 8)))]
+    hc = e.host_chunks()
+    assert all(hc["updated"][int(e.host_map()["chunkIndex"][t])] for t in upd if e.host_map()["flag"][t]), "the refused call consumed the updated flags"
+    e.sync(1, 1)
     assert check(e, d, o, 300, "terrain after edits") > 1000
     e.close()
+
+
+def _wave_pool(dn, light_kernel, slots):
+    """the wavefront kernels with a context pool far smaller than the dispatch: slots are recycled pass after pass"""
+    if light_kernel == "wave":
+        dn.lib().DN_b200_set_wave_slots(slots)
+
+
+def test_sparse_balls_against_oracle(dn, oracle_mod, light_kernel):
+    """config 3 in miniature (sparse map: ~20 % of the tiles hold a ball, diffuse / glossy / emissive; rays of very different
+    length, specular propagation of the visible bit) against the ORACLE through the full frame protocol, every lighting kernel,
+    the wavefront pool forced down to 640 slots so that it is recycled many times per dispatch."""
+    from doonengine_b200 import scenes
+    tiles = (20, 20, 20)
+    n = scenes.native_count("sparse", tiles)
+    e = dn.Engine(map_size=tiles, min_chunks=n + 16)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=n + 16)
+    scenes.build_native(e, "sparse", tiles, **scenes.sparse_camera(tiles))          # the bench's bulk path (DN_b200_set_chunks)
+    scenes.build(o, scenes.sparse_balls(tiles), **scenes.sparse_camera(tiles))
+    _wave_pool(dn, light_kernel, 640)
+    try:
+        _protocol(e, o, frames=3, w=640, h=368)
+        assert e.num_requests() > 2000
+    finally:
+        dn.lib().DN_b200_set_wave_slots(0)
+        e.close()
+        o.close()
+
+
+def test_dense_corridors_against_oracle(dn, oracle_mod, light_kernel):
+    """config 5 in miniature (every voxel solid, mirror-like material, a lattice of one-tile corridors; 15 specular rays of up to
+    two segments per voxel that faces the camera) against the oracle, every lighting kernel, small wavefront pool."""
+    from doonengine_b200 import scenes
+    tiles = (8, 8, 8)
+    n = scenes.native_count("dense", tiles)
+    e = dn.Engine(map_size=tiles, min_chunks=n + 16)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=n + 16)
+    scenes.build_native(e, "dense", tiles, **scenes.dense_camera(tiles))
+    scenes.build(o, scenes.dense_corridors(tiles), **scenes.dense_camera(tiles))
+    _wave_pool(dn, light_kernel, 640)
+    try:
+        _protocol(e, o, frames=3, w=640, h=368)
+        assert e.num_requests() > 1000
+    finally:
+        dn.lib().DN_b200_set_wave_slots(0)
+        e.close()
+        o.close()
+
+
+def test_bulk_edit_stream_against_oracle(dn, oracle_mod):
+    """config 4 in miniature: the bench's edit stream (bench.frame_edits: half removals, half sets, uniform in the box) applied
+    through the BULK call DN_b200_set_voxels on the CUDA side and voxel by voxel on the oracle, 1 000 edits before each of 4 frames:
+    re-uploaded chunks, requests (incl. the stale pre-edit group counts, voxel.c:757 vs :761), lit records and pixels."""
+    import bench
+    from doonengine_b200 import scenes
+    tiles = (12, 8, 12)
+    e = dn.Engine(map_size=tiles, min_chunks=64)   # small pools: growth + allocator churn under edits
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    for eng in (e, o):
+        scenes.build(eng, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+        eng.sync(1, 1)
+    _compare_state(e, records_by_tile(o), "after upload")
+    for k in range(4):
+        pos, vox = bench.frame_edits(k, tiles, n=1000)
+        assert e.set_voxels(pos, vox) == 1000
+        for p, v in zip(pos, vox):
+            o.set_voxel(tuple(int(x) // 8 for x in p), tuple(int(x) % 8 for x in p), int(v[0]), int(v[1]))
+        gi, gh = e.draw(W, H, want_hits=True)   # the draw still sees the pre-edit device map on both sides
+        oi, oh = o.draw(W, H, want_hits=True)
+        assert_hits_equal(gh, oh, "frame %d" % k)
+        assert_images_close(gi, oi, "frame %d" % k)
+        for eng in (e, o):
+            eng.sync(2, 1)
+        assert np.array_equal(e.requests(), o.requests()), "frame %d: request lists differ" % k
+        for eng in (e, o):
+            eng.update_lighting(1, 1000, frame_time(k))
+        _compare_state(e, records_by_tile(o), "frame %d" % k)
+    st = e.stats()
+    assert st["nodeSplits"] > 0 and st["usedNodes"] == st["residentChunks"]
+    # the gpuVoxelLayout mirror (voxel.h:108-117): every resident chunk owns exactly one node that holds its records; free and used
+    # nodes tile the pool without overlap
+    L = dn.lib()
+    assert e.vol.contents.numVoxelNodes == 0 and not e.vol.contents.gpuVoxelLayout
+    assert L.DN_b200_mirror_voxel_layout(e.vol)
+    nn = int(e.vol.contents.numVoxelNodes)
+    nodes = dn._view(e.vol.contents.gpuVoxelLayout, np.dtype([("size", "<u4"), ("_p", "<u4"), ("startPos", "<u8"), ("chunkPos", "<i4", 3), ("_q", "<u4")]), nn)
+    assert nn == st["usedNodes"] + st["freeNodes"]
+    assert np.array_equal(nodes["startPos"][1:], (nodes["startPos"] + nodes["size"])[:-1]) and int(nodes["startPos"][0]) == 0
+    assert int(nodes["startPos"][-1] + nodes["size"][-1]) == st["recordTop"]
+    used = nodes[nodes["chunkPos"][:, 0] >= 0]
+    state = records_by_tile(e)
+    owner_tiles = used["chunkPos"][:, 0] + tiles[0] * (used["chunkPos"][:, 1] + tiles[1] * used["chunkPos"][:, 2])
+    assert sorted(int(t) for t in owner_tiles) == [int(t) for t in state["tiles"]]
+    by_tile = dict(zip((int(t) for t in state["tiles"]), (int(c) for c in state["counts"])))
+    for nd, t in zip(used, owner_tiles):
+        assert by_tile[int(t)] <= int(nd["size"]) and (int(nd["size"]) == 16 or by_tile[int(t)] > int(nd["size"]) // 2)
+    e.sync(1, 1)
+    assert L.DN_b200_mirror_voxel_layout(e.vol)
+    e.set_voxel((0, 0, 0), (0, 0, 0), 0x007FFF7F, 0x80402000)
+    e.sync(1, 1)  # the pool changes: the snapshot is dropped, never left dangling
+    assert e.vol.contents.numVoxelNodes == 0 and not e.vol.contents.gpuVoxelLayout
+    e.close()
+    o.close()
+
+
+def test_terrain_64_frames(dn, oracle_mod):
+    """config 2's frame count (64 accumulated frames, one diffuse sample each) on a slice of its map: the running mean and the
+    sample counters stay identical to the oracle's all the way (state compared every 8th frame, requests every frame)."""
+    from doonengine_b200 import scenes
+    tiles = (12, 8, 12)
+    e = dn.Engine(map_size=tiles, min_chunks=64)
+    o = oracle_mod.OracleEngine(map_size=tiles, min_chunks=64)
+    for eng in (e, o):
+        scenes.build(eng, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+        eng.sync(1, 1)
+    for k in range(64):
+        if k % 8 == 0 or k == 63:
+            gi, gh = e.draw(256, 144, want_hits=True)
+            oi, oh = o.draw(256, 144, want_hits=True)
+            assert_hits_equal(gh, oh, "frame %d" % k)
+            assert_images_close(gi, oi, "frame %d" % k)
+        else:
+            e.draw(256, 144)
+            o.draw(256, 144)
+        for eng in (e, o):
+            eng.sync(2, 1)
+        assert np.array_equal(e.requests(), o.requests()), "frame %d: request lists differ" % k
+        for eng in (e, o):
+            eng.update_lighting(1, 1000, frame_time(k))
+        if k % 8 == 7:
+            info = _compare_state(e, records_by_tile(o), "frame %d" % k)
+    assert int(records_by_tile(e)["samples"].max()) == 64 and info["exact"]
+    e.close()
+    o.close()
+
+
+def test_batched_picking_against_reference_goldens(dn, light_kernel):
+    """DN_b200_step_map_batch against picks made by the REFERENCE's own DN_step_map (voxel.c:1195-1272, compiled in place as
+    oracle/_ref; tests/golden/picks.npz written by tests/golden/make_golden.py): hit flag, hit cell, face normal, voxel."""
+    if light_kernel != "warp":
+        pytest.skip("no lighting involved")
+    from doonengine_b200 import scenes
+    g = np.load(os.path.join(GOLDEN, "picks.npz"))
+    for name in ("demo", "terrain"):
+        if name == "demo":
+            e = dn.Engine(voxvol=DEMO, min_chunks=256)
+        else:
+            tiles = tuple(int(x) for x in g["terrain_tiles"])
+            e = dn.Engine(map_size=tiles, min_chunks=600)
+            scenes.build(e, scenes.terrain(tiles), **scenes.terrain_camera(tiles))
+        e.sync(1, 1)
+        steps = int(g[name + "_steps"])
+        got = e.step_map_batch(g[name + "_dirs"], g[name + "_origins"], steps)
+        hit = g[name + "_hit"].astype(bool)
+        assert np.array_equal(got["hit"].astype(bool), hit), name
+        assert np.array_equal(got["normal"], g[name + "_normal"]), name
+        assert np.array_equal(got["pos"][hit], g[name + "_pos"][hit]), name
+        assert np.array_equal(got["voxel"]["material"][hit], g[name + "_material"][hit]), name
+        assert np.array_equal(got["voxel"]["albedo"][hit], g[name + "_albedo"][hit]), name
+        assert np.array_equal(got["voxel"]["normal"][hit].view(np.uint32), g[name + "_vnormal"][hit].view(np.uint32)), name
+        assert hit.sum() > 1000
+        e.close()
