@@ -110,7 +110,7 @@ HOST_HANDLE_DT = np.dtype([("flag", "u1"), ("_pad", "u1", 3), ("chunkIndex", "<u
 MATERIAL_DT = np.dtype([("pad", "<f4", 2), ("emissive", "<u4"), ("opacity", "<f4"), ("refractIndex", "<f4"),
                         ("specular", "<f4"), ("reflectType", "<u4"), ("shininess", "<u4")])
 SLOT_DT = np.dtype([("mask", "<u4", 16), ("voxelBase", "<u4"), ("numVoxels", "<u4"), ("numSamples", "<u4"),
-                    ("mapIndex", "<u4"), ("prefix", "<u2", 16), ("pos", "<i4", 3), ("bbox", "<u4")])
+                    ("matIds", "<u4"), ("prefix", "<u2", 16), ("pos", "<i4", 3), ("bbox", "<u4")])
 VOXEL_DT = np.dtype([("material", "u1"), ("normal", "<f4", 3), ("albedo", "u1", 3)], align=True)  # DNvoxel (voxel.h:44-52), 20 bytes
 HIT_DT = np.dtype([("status", "<i4"), ("mapIndex", "<u4"), ("localIndex", "<u4"), ("recordIndex", "<u4")])
 assert HOST_CHUNK_DT.itemsize == 4120 and HOST_HANDLE_DT.itemsize == 8 and MATERIAL_DT.itemsize == 32 and SLOT_DT.itemsize == 128

@@ -181,6 +181,32 @@ void fill_scene(VolumeImpl* v, DnbScene* s)
 	memcpy(s->ambient, &vol->ambientLightStrength, 12);
 }
 
+static void exact_opaque_bits(const DNvolume* vol, uint32_t bits[8]);
+
+/* uploads the material table (it travels with every draw and lighting call, as upstream: voxel.c:823-824) and keeps the slots'
+ * DNB_BBOX_OPAQUE flags true: they were derived from the opacities of v->opaqueBits; when the application has changed an opacity
+ * across 1.0 since, every slot's flag is re-derived on the device before anything traces */
+bool sync_materials(VolumeImpl* v, cudaStream_t s)
+{
+	DNvolume* vol = &v->pub;
+	bool ok = cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
+	uint32_t bits[8];
+	exact_opaque_bits(vol, bits);
+	if(!v->opaqueBitsValid || memcmp(bits, v->opaqueBits, sizeof(bits)) != 0)
+	{
+		memcpy(v->opaqueBits, bits, sizeof(bits));
+		v->opaqueBitsValid = true;
+		if(v->slotTop > 0)
+		{
+			/* the upload stream may still be scattering slots packed against the old table */
+			cuda_ok(cudaEventRecord(ctx().evUploadDone, ctx().uploadStream), "event record");
+			cuda_ok(cudaStreamWaitEvent(s, ctx().evUploadDone, 0), "stream wait");
+			ok = ok && cuda_ok(dnb_launch_refresh_opaque(v->slots.ptr, v->slotTop, bits, s), "opaque-flag refresh");
+		}
+	}
+	return ok;
+}
+
 /* ---- timing helpers: device time of a kernel group, only when DN_b200_enable_timing(true) ---- */
 /* host wall-clock of the phases of a writing sync (always on: four clock reads per sync) */
 static inline double host_now_ms()
@@ -244,6 +270,17 @@ static void opaque_table(const DNvolume* vol, uint8_t out[256])
 		out[m] = (m != DN_MATERIAL_EMPTY && !(vol->materials[m].opacity < 1.0f)) ? 1 : 0;
 }
 
+/* per material: is a hit on it an OPAQUE hit?  voxelShared.comp:351 tests `material.opacity == 1.0` exactly (1.5 or NaN are "transparent"
+ * there although they hide faces at packing): 256 bits, bit m of word m / 32 */
+static void exact_opaque_bits(const DNvolume* vol, uint32_t bits[8])
+{
+	for(int w = 0; w < 8; w++)
+		bits[w] = 0;
+	for(int m = 0; m < 256; m++)
+		if(vol->materials[m].opacity == 1.0f)
+			bits[m >> 5] |= 1u << (m & 31);
+}
+
 /* transpose of an 8x8 bit matrix held as 8 bytes (byte i, bit j  <->  byte j, bit i) */
 static inline uint64_t transpose8(uint64_t x)
 {
@@ -258,11 +295,13 @@ static inline uint64_t transpose8(uint64_t x)
  * Same result as _DN_chunk_to_gpu + _DN_check_face_visible (voxel.c:1391-1461) voxel by voxel, computed on bit rows: the chunk
  * is stored [x][y][z], so the 8 voxels of an (x, y) row are one cache line; each row becomes two bytes (solid, opaque) and the
  * six-neighbour test becomes a handful of ANDs per row instead of six dependent loads per voxel. */
-static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const DNchunk* c, uint32_t mapIndex, DnbSlot* slot, uint4* records)
+static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const uint32_t exactOpaque[8], const DNchunk* c, uint32_t mapIndex, DnbSlot* slot, uint4* records)
 {
 	const uint8_t* lut = albedo_lut();
 	memset(slot, 0, sizeof(*slot));
-	slot->mapIndex = mapIndex;
+	(void)mapIndex;
+	uint32_t matIds = 0xFFFFFFFFu, numMats = 0; /* distinct materials of the surface voxels, first four */
+	bool mixed = false;
 	slot->pos[0] = c->pos.x; slot->pos[1] = c->pos.y; slot->pos[2] = c->pos.z;
 	slot->numSamples = 0; /* an edit restarts the accumulation (voxel.c:1401) */
 
@@ -315,6 +354,15 @@ static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const
 				word &= word - 1;
 				const int x = bit & 7, y = 4 * q + (bit >> 3);
 				const DNcompressedVoxel vx = c->voxels[x][y][z];
+				const uint32_t mat = vx.normal >> 24;
+				if(((matIds & 0xFFu) != mat) && (((matIds >> 8) & 0xFFu) != mat) && (((matIds >> 16) & 0xFFu) != mat) && ((matIds >> 24) != mat))
+				{
+					if(numMats < 4)
+						matIds = (matIds & ~(0xFFu << (8 * numMats))) | (mat << (8 * numMats));
+					else
+						mixed = true;
+					numMats++;
+				}
 				uint4 rec;
 				rec.x = vx.normal;
 				rec.y = ((uint32_t)lut[vx.albedo >> 24] << 24) | ((uint32_t)lut[(vx.albedo >> 16) & 0xFF] << 16) | ((uint32_t)lut[(vx.albedo >> 8) & 0xFF] << 8);
@@ -339,6 +387,7 @@ static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const
 				zb |= 1u << z;
 		}
 	}
+	slot->matIds = mixed ? 0xFFFFFFFFu : matIds;
 	if(n == 0)
 		slot->bbox = 0; /* nothing to hit; offsets of zero = no culling */
 	else
@@ -349,6 +398,20 @@ static uint32_t pack_chunk(const DNvolume* vol, const uint8_t opaque[256], const
 		for(int a = 0; a < 3; a++)
 			bb |= ((7u - mx[a]) << (3 * a)) | (mn[a] << (9 + 3 * a));
 		slot->bbox = bb;
+	}
+	/* DNB_BBOX_OPAQUE (layout.h): every listed material is opaque in the table in force */
+	if(mixed)
+		slot->bbox |= DNB_BBOX_MIXED;
+	else
+	{
+		bool all = true;
+		for(uint32_t k = 0; k < numMats && k < 4; k++)
+		{
+			const uint32_t m = (matIds >> (8 * k)) & 0xFFu;
+			all = all && ((exactOpaque[m >> 5] >> (m & 31)) & 1u);
+		}
+		if(all)
+			slot->bbox |= DNB_BBOX_OPAQUE;
 	}
 	return n;
 }
@@ -365,8 +428,10 @@ extern "C" int DN_b200_pack_chunk(DNvolume* vol, DNivec3 mapPos, void* slotOut12
 	if(vol->map[mapIndex].flag == 0)
 		return -1;
 	uint8_t opaque[256];
+	uint32_t exact[8];
 	dnb::opaque_table(vol, opaque);
-	return (int)dnb::pack_chunk(vol, opaque, &vol->chunks[vol->map[mapIndex].chunkIndex], (uint32_t)mapIndex, (DnbSlot*)slotOut128, (uint4*)recordsOut);
+	dnb::exact_opaque_bits(vol, exact);
+	return (int)dnb::pack_chunk(vol, opaque, exact, &vol->chunks[vol->map[mapIndex].chunkIndex], (uint32_t)mapIndex, (DnbSlot*)slotOut128, (uint4*)recordsOut);
 }
 
 namespace dnb
@@ -548,6 +613,9 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 	/* parallel pack: worker t owns a contiguous range of items and packs their records back to back into its arena */
 	uint8_t opaque[256];
 	opaque_table(vol, opaque);
+	/* the flags are packed against the table the DEVICE's flags are consistent with (v->opaqueBits); if the application has changed
+	 * opacities since, the next draw / lighting call notices and re-derives every slot's flag, these included (sync_materials) */
+	const uint32_t* exactOpaque = v->opaqueBits;
 	unsigned workers = 1;
 	if(count >= 128)
 		workers = std::max(1u, std::min<unsigned>(PackPool::get().size(), (unsigned)(count / 64)));
@@ -567,7 +635,7 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 				memset(&hHeaders[i], 0, sizeof(DnbSlot));
 				continue;
 			}
-			cursor += pack_chunk(vol, opaque, &vol->chunks[items[i].chunkIndex], items[i].tile, &hHeaders[i], hRecords + cursor);
+			cursor += pack_chunk(vol, opaque, exactOpaque, &vol->chunks[items[i].chunkIndex], items[i].tile, &hHeaders[i], hRecords + cursor);
 		}
 		arenaUsed[t] = cursor - begin * 512;
 	};
@@ -1176,7 +1244,7 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 	ScopedTimer timer(&v->stats.lastDrawMs, s);
 
 	/* materials travel with every draw, as upstream (voxel.c:823-824) */
-	cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
+	sync_materials(v, s);
 
 	/* voxel.c:845-853 */
 	Mat4 V, P, C;
@@ -1441,7 +1509,7 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	}
 
 	ScopedTimer timer(&v->stats.lastLightMs, s);
-	bool ok = cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
+	bool ok = sync_materials(v, s);
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
 	/* a slice that is not the last one ends on a CTA boundary (slice_len is a multiple of 4); the last CTA of the list is cut by numRequests */
 	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));

@@ -95,6 +95,8 @@ struct VolumeImpl
 	uint32_t*      pinnedScalars = nullptr;    /* read-back of the request count */
 	DnbCounters*   counters = nullptr;         /* device, NULL when instrumentation is off */
 	bool           forcedDirty = false;
+	uint32_t       opaqueBits[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* materials with opacity == 1.0 in the table the slots' DNB_BBOX_OPAQUE flags were derived from */
+	bool           opaqueBitsValid = false;
 
 	size_t requestsValid = 0;                  /* requests on the device from the last reading sync */
 	size_t stagedRequests = 0;                 /* requests covered by the staging array (last compute phase) */
@@ -141,6 +143,7 @@ void touch_tile(VolumeImpl* v, size_t mapIndex);
 bool device_create(VolumeImpl* v);   /* allocates the per-tile arrays for pub.mapSize */
 void device_destroy(VolumeImpl* v);
 void fill_scene(VolumeImpl* v, DnbScene* s);
+bool sync_materials(VolumeImpl* v, cudaStream_t s);
 
 } // namespace dnb
 

@@ -52,6 +52,9 @@ cudaError_t dnb_launch_pick(const DnbScene* scene, const float* dirs, const floa
 cudaError_t dnb_launch_peer_barrier(const DnbPeerTable* peers, uint32_t epoch, uint32_t* status, cudaStream_t stream);
 cudaError_t dnb_launch_peer_or_visible(const DnbPeerTable* peers, uint32_t* visible, uint32_t words, cudaStream_t stream);
 
+/* upload.cu: re-derives DNB_BBOX_OPAQUE of slots[0, numSlots) from their matIds and the 256-bit table opaqueBits (layout.h) */
+cudaError_t dnb_launch_refresh_opaque(DnbSlot* slots, uint32_t numSlots, const uint32_t opaqueBits[8], cudaStream_t stream);
+
 uint32_t    dnb_compact_num_blocks(uint32_t numTiles);
 /* hostTotal: NULL or a device-accessible pinned host word that also receives the total (zero-copy store) */
 cudaError_t dnb_launch_compact_count(const DnbScene* scene, const uint32_t* forced, uint32_t split, uint32_t frameNum, uint32_t* blockCounts, uint32_t* blockOffsets, uint32_t* grandTotal,

@@ -42,12 +42,20 @@ typedef struct DNB_ALIGN(128) DnbSlot
 	uint32_t voxelBase;   /* index of the chunk's first record */
 	uint32_t numVoxels;   /* number of records */
 	uint32_t numSamples;  /* lighting dispatches accumulated (Chunk.numIndirectSamples) */
-	uint32_t mapIndex;    /* owner tile */
+	uint32_t matIds;      /* the distinct material ids of the chunk's surface voxels, one per byte, unused bytes = 0xFF (never a voxel's material:
+	                         255 = empty); more than four: 0xFFFFFFFF and DNB_BBOX_MIXED in bbox */
 	uint16_t prefix[16];  /* records before mask word i */
 	int32_t  pos[3];      /* owner tile position */
 	uint32_t bbox;        /* bounding box of the surface voxels, ready to use as cell offsets (trace.cuh "exact chunk cull"):
-	                         bits [3a, 3a+3) = 7 - max on axis a (rays stepping up), bits [9+3a, 12+3a) = min on axis a (rays stepping down) */
+	                         bits [3a, 3a+3) = 7 - max on axis a (rays stepping up), bits [9+3a, 12+3a) = min on axis a (rays stepping down);
+	                         DNB_BBOX_MIXED: more than four materials (matIds does not list them);
+	                         DNB_BBOX_OPAQUE: every material listed in matIds has opacity == 1.0 in the material table the device holds, so
+	                         a set voxel bit is an opaque hit (voxelShared.comp:351) without looking at the record -- kept true by the host:
+	                         set at packing, re-derived for every slot by dn_refresh_opaque_kernel when the table's opacities change */
 } DnbSlot;
+
+#define DNB_BBOX_MIXED  0x40000000u
+#define DNB_BBOX_OPAQUE 0x80000000u
 
 /* material as the kernels read it; 32 bytes like DNmaterial, same field order (voxel.h:82-94) */
 typedef struct DnbMaterial

@@ -19,6 +19,8 @@
  * Slot layout: structure of arrays, 15 planes of P uint4 (240 bytes per slot), so that both kernels move whole 16-byte words
  * and the serve kernel's accesses are fully coalesced.
  */
+#include "ray_step.cuh"
+
 enum : uint32_t
 {
 	WV_REC = 0,   /* the voxel's record */
@@ -34,11 +36,11 @@ enum : uint32_t
 	WR_CELL = 10, /* ray: tile-level cell (int) */
 	WH_POS = 11,  /* result: hit position (or the origin), flags (WF_HIT | WF_TRIPPED | WF_INSIDE) */
 	WH_COL = 12,  /* result: colorAdd.xyz, colorMult */
-	WH_VOX = 13,  /* result: record hit (written / read only on a hit) */
+	WH_VOX = 13,  /* result: record hit (written / read only on a hit); with WF_DEFERRED: {slot, local index, mask word} -- the serve kernel fetches the record (ray_step.cuh) */
 	WH_ST = 14,   /* result: lastVoxID, lastVoxRefract (written / read only with WF_INSIDE) */
 	WAVE_PLANES = 15
 };
-enum : uint32_t { WF_READY = 1u, WF_TRIPPED = 2u, WF_HIT = 1u, WF_INSIDE = 4u };
+enum : uint32_t { WF_READY = 1u, WF_TRIPPED = 2u, WF_HIT = 1u, WF_INSIDE = 4u, WF_DEFERRED = 8u };
 /* schedule word: kind[0:2) idx[2:8) seg[8:16) firstSample[16] sourceVisible[17] reflectType[18:26) active[31] */
 #define WS_ACTIVE 0x80000000u
 
@@ -95,7 +97,11 @@ __global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbSc
 		L.st.vox = make_uint4(0, 0, 0, 0);
 		L.st.hitMapIndex = L.st.hitLocalIndex = L.st.hitRecord = 0;
 		if(L.hit)
+		{
 			L.st.vox = PL(WH_VOX);
+			if(hPos.w & WF_DEFERRED)
+				L.st.vox = ray_deferred_record(S, L.st.vox, nullptr); /* the step kernel ended the ray on the voxel's bit alone */
+		}
 		if(hPos.w & WF_INSIDE)
 		{
 			const uint4 hSt = PL(WH_ST);
@@ -333,6 +339,115 @@ __global__ void __launch_bounds__(128, WAVE_MIN_BLOCKS) dn_wave_step_kernel(DnbS
 	}
 }
 
+/* ---- the lock-step stepping kernel (ray_step.cuh): same slot planes, same per-warp double-buffered cp.async prefetch and dynamic
+ * ranges as dn_wave_step_kernel; every lane advances its ray by one cell per trip through ONE loop body (chunk exit, block / layer
+ * change, chunk entry, voxel test, step -- no votes, no phases), hits in all-opaque chunks end the ray without touching the record,
+ * idle lanes are refilled once `refillMin` of them have gathered (or nothing else runs). ---- */
+#ifndef WAVE2_MIN_BLOCKS
+#define WAVE2_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, WAVE2_MIN_BLOCKS) dn_wave_step2_kernel(DnbScene S, uint4* __restrict__ ctx, uint32_t P, uint32_t* __restrict__ cursor, int refillMin)
+{
+	__shared__ uint4 s_rays[4][2][5 * 32];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t ltMask = (1u << lane) - 1u;
+
+	uint32_t cur = 0, next = 0, end = 0, preBase = 0xFFFFFFFFu;
+	{
+		uint32_t base = 0;
+		if(lane == 0)
+			base = atomicAdd(cursor, WAVE_GRAB);
+		preBase = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if(preBase >= P)
+			return;
+		wave_prefetch(s_rays[warp][1], ctx, P, preBase, lane);
+	}
+
+	RayLane L;
+	bool idle = true;
+	uint32_t slot = 0;
+	L.hit = false;
+
+	for(;;)
+	{
+		const uint32_t mI = __ballot_sync(0xFFFFFFFFu, idle);
+		if(mI != 0u && (__popc(mI) >= refillMin || mI == 0xFFFFFFFFu))
+		{
+			if(next >= end && preBase < P)
+			{
+				/* switch to the prefetched range and start fetching the one after it */
+				__pipeline_wait_prior(0);
+				__syncwarp();
+				cur ^= 1u;
+				next = preBase;
+				end = preBase + WAVE_GRAB < P ? preBase + WAVE_GRAB : P;
+				uint32_t base = 0;
+				if(lane == 0)
+					base = atomicAdd(cursor, WAVE_GRAB);
+				preBase = __shfl_sync(0xFFFFFFFFu, base, 0);
+				if(preBase < P)
+					wave_prefetch(s_rays[warp][cur ^ 1u], ctx, P, preBase, lane);
+			}
+			if(next < end)
+			{
+				if(idle)
+				{
+					const uint32_t idx = next + (uint32_t)__popc(mI & ltMask);
+					if(idx < end)
+					{
+						const uint4* row = s_rays[warp][cur] + (idx & 31u);
+						const uint4 rInv = row[2 * 32];
+						if(rInv.w & WF_READY)
+						{
+							const uint4 rDir = row[0], rPos = row[1 * 32], rSide = row[3 * 32], rCell = row[4 * 32];
+							slot = idx;
+							L.dir = xyz_of(rDir);
+							L.rayPos = xyz_of(rPos);
+							L.lastVoxID = rDir.w;
+							L.lastVoxRefract = __uint_as_float(rPos.w);
+							L.tripped = (rInv.w & WF_TRIPPED) != 0u;
+							/* ray_begin with the serve kernel's precomputed tile-level DDA start */
+							L.delta = abs3(xyz_of(rInv));
+							L.step.x = isgn(L.dir.x); L.step.y = isgn(L.dir.y); L.step.z = isgn(L.dir.z);
+							L.pos.x = (int)rCell.x; L.pos.y = (int)rCell.y; L.pos.z = (int)rCell.z;
+							L.side = xyz_of(rSide);
+							L.tl = 0.0f;
+							L.g = 0;
+							L.lv = 0;
+							L.blk.x = L.blk.y = L.blk.z = 0x40000000;
+							L.word = 0;
+							L.off.x = L.off.y = L.off.z = 0;
+							L.colorAdd = splat3(0.0f);
+							L.colorMult = 1.0f;
+							L.ignoreFirst = true;
+							L.hit = false;
+							L.deferred = false;
+							L.vox = make_uint4(0, 0, 0, 0);
+							idle = false;
+						}
+					}
+				}
+				next += (uint32_t)__popc(mI);
+			}
+			else if(mI == 0xFFFFFFFFu)
+				break; /* no range left (the cursor is past the pool) and every lane is idle */
+		}
+
+		if(!idle && ray_iter<true>(S, L))
+		{
+			/* the segment is over: its result goes back to the slot, the lane is free */
+			const bool inside = L.lastVoxID != 255u;
+			ctx[(size_t)WH_POS * P + slot] = f3w(L.rayPos, (L.hit ? WF_HIT : 0u) | (L.tripped ? WF_TRIPPED : 0u) | (inside ? WF_INSIDE : 0u) | (L.deferred ? WF_DEFERRED : 0u));
+			ctx[(size_t)WH_COL * P + slot] = f3w(L.colorAdd, __float_as_uint(L.colorMult));
+			if(L.hit)
+				ctx[(size_t)WH_VOX * P + slot] = L.vox;
+			if(inside)
+				ctx[(size_t)WH_ST * P + slot] = make_uint4(L.lastVoxID, __float_as_uint(L.lastVoxRefract), 0, 0);
+			idle = true;
+		}
+	}
+}
+
 /* host side of one wavefront dispatch.  Passes are queued without waiting; every pass copies its count of live slots to a
  * pinned ring and the host looks at the count of the pass WAVE_LAG passes back before queueing another, so the device never
  * runs dry and at most WAVE_LAG empty passes are queued after the last voxel has finished. */
@@ -341,7 +456,7 @@ struct DnbWaveHost
 {
 	uint32_t*   pinned = nullptr; /* ring of 8 counts */
 	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-	int         stepCtas = 0;
+	int         stepCtas = 0, step2Ctas = 0;
 };
 static DnbWaveHost g_wave;
 
@@ -369,6 +484,10 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dn_wave_step_kernel, 128, 0) != cudaSuccess || perSm < 1)
 			perSm = WAVE_MIN_BLOCKS;
 		g_wave.stepCtas = sms * perSm;
+		int perSm2 = WAVE2_MIN_BLOCKS;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm2, dn_wave_step2_kernel, 128, 0) != cudaSuccess || perSm2 < 1)
+			perSm2 = WAVE2_MIN_BLOCKS;
+		g_wave.step2Ctas = sms * perSm2;
 	}
 	DnbFlatTuning tuning;
 	{
@@ -386,8 +505,11 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 	if((e = cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), stream)) != cudaSuccess)
 		return e;
 
+	/* which stepping kernel: 2 = lock-step (default), 1 = the two-phase kernel it replaced (kept for A/B runs: $DN_B200_WAVE_STEP=1) */
+	static const int stepKind = getenv("DN_B200_WAVE_STEP") && atoi(getenv("DN_B200_WAVE_STEP")) == 1 ? 1 : 2;
+	static const int refillMin = [] { const char* v = getenv("DN_B200_WAVE_REFILL"); return v && atoi(v) > 0 ? atoi(v) : 4; }();
 	const uint32_t totalItems = numCtas * 128u;
-	const uint32_t stepCtas = std::min<uint32_t>((uint32_t)g_wave.stepCtas, (P + 4u * WAVE_GRAB - 1u) / (4u * WAVE_GRAB));
+	const uint32_t stepCtas = std::min<uint32_t>((uint32_t)(stepKind == 2 ? g_wave.step2Ctas : g_wave.stepCtas), (P + 4u * WAVE_GRAB - 1u) / (4u * WAVE_GRAB));
 
 	static const bool trace = getenv("DN_B200_WAVE_TRACE") != nullptr;
 	uint32_t pass = 0;
@@ -410,7 +532,10 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 			return e;
 		if((e = cudaEventRecord(g_wave.ev[pass & 7u], stream)) != cudaSuccess)
 			return e;
-		{ DNB_LAUNCHED(1); dn_wave_step_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters + 3, tuning); }
+		if(stepKind == 2)
+			{ DNB_LAUNCHED(1); dn_wave_step2_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters + 3, refillMin); }
+		else
+			{ DNB_LAUNCHED(1); dn_wave_step_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters + 3, tuning); }
 		if((e = cudaGetLastError()) != cudaSuccess)
 			return e;
 	}

@@ -59,3 +59,43 @@ extern "C" cudaError_t dnb_launch_scatter(const DnbUploadItem* items, const DnbS
 	{ DNB_LAUNCHED(1); dn_scatter_chunks_kernel<<<(numItems + 7) / 8, 256, 0, stream>>>(items, headers, blobRecords, numItems, mapSize[0], mapSize[1], blocks[0], blocks[1], tileSlot, occ64, visible, slots, records); }
 	return cudaGetLastError();
 }
+
+/* the slots' "every material of this chunk is opaque" flag against a new material table (layout.h DNB_BBOX_OPAQUE): one thread per slot */
+struct DnbOpaqueBits { uint32_t w[8]; };
+__global__ void __launch_bounds__(256) dn_refresh_opaque_kernel(DnbSlot* __restrict__ slots, uint32_t numSlots, DnbOpaqueBits bits)
+{
+	const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+	if(i >= numSlots)
+		return;
+	const uint32_t bbox = slots[i].bbox, ids = slots[i].matIds;
+	bool all = !(bbox & DNB_BBOX_MIXED);
+#pragma unroll
+	for(int k = 0; k < 4; k++)
+	{
+		const uint32_t m = (ids >> (8 * k)) & 0xFFu;
+		if(m != 0xFFu)
+		{
+			/* static indexing of the parameter words */
+			uint32_t word = 0;
+#pragma unroll
+			for(int w = 0; w < 8; w++)
+				if((m >> 5) == (uint32_t)w)
+					word = bits.w[w];
+			all = all && ((word >> (m & 31u)) & 1u);
+		}
+	}
+	const uint32_t fresh = (bbox & ~DNB_BBOX_OPAQUE) | (all ? DNB_BBOX_OPAQUE : 0u);
+	if(fresh != bbox)
+		slots[i].bbox = fresh;
+}
+
+extern "C" cudaError_t dnb_launch_refresh_opaque(DnbSlot* slots, uint32_t numSlots, const uint32_t opaqueBits[8], cudaStream_t stream)
+{
+	if(numSlots == 0)
+		return cudaSuccess;
+	DnbOpaqueBits b;
+	for(int w = 0; w < 8; w++)
+		b.w[w] = opaqueBits[w];
+	{ DNB_LAUNCHED(1); dn_refresh_opaque_kernel<<<(numSlots + 255) / 256, 256, 0, stream>>>(slots, numSlots, b); }
+	return cudaGetLastError();
+}
