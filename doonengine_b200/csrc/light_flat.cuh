@@ -557,10 +557,14 @@ __global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_fla
 			bool start = false;
 			if(state == ST_END)
 				start = flat_ray_ended(S, T, L, state);
+			/* lanes without a voxel take the next work items.  Two rounds, because an item can turn out to hold no voxel (tail of a
+			 * chunk's last group).  `need` -- not `state` -- says who still fetches: a lane that has just been given a voxel stays in
+			 * ST_FETCH until flat_start_ray below, and must NOT take (and thereby drop) a second item. */
+			bool need = state == ST_FETCH;
 #pragma unroll 1
 			for(int round = 0; round < 2; round++)
 			{
-				const uint32_t mF = __ballot_sync(0xFFFFFFFFu, state == ST_FETCH);
+				const uint32_t mF = __ballot_sync(0xFFFFFFFFu, need);
 				if(mF == 0u)
 					break;
 				uint32_t base = 0;
@@ -568,13 +572,19 @@ __global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_fla
 				if((int)lane == leader)
 					base = atomicAdd(workCounter, (uint32_t)__popc(mF));
 				base = __shfl_sync(0xFFFFFFFFu, base, leader);
-				if(state == ST_FETCH)
+				if(need)
 				{
 					const uint32_t j = base + (uint32_t)__popc(mF & ltMask);
 					if(j < totalItems)
+					{
 						start = flat_setup_voxel(S, T, requests, numRequests, firstCta, ctaStride, j, L, state);
+						need = !start;
+					}
 					else
+					{
 						state = ST_DONE;
+						need = false;
+					}
 				}
 			}
 			if(start)

@@ -115,11 +115,14 @@ __global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbSc
 	}
 
 	/* free slots take the next voxels of the dispatch (two rounds: an item can turn out to hold no voxel).  ONE atomic per CTA
-	 * and round: with one per warp the 10^5 same-address atomics of a pass were a quarter of the kernel's stall samples */
+	 * and round: with one per warp the 10^5 same-address atomics of a pass were a quarter of the kernel's stall samples.
+	 * `need` -- not `state` -- says who still fetches: a slot that has just been given a voxel keeps state ST_FETCH (nothing sets it
+	 * before the store below) and must NOT take, and thereby drop, a second item. */
+	bool need = state == ST_FETCH;
 #pragma unroll 1
 	for(int round = 0; round < 2; round++)
 	{
-		const uint32_t mF = __ballot_sync(0xFFFFFFFFu, state == ST_FETCH);
+		const uint32_t mF = __ballot_sync(0xFFFFFFFFu, need);
 		if(lane == 0)
 			s_warpCount[threadIdx.x >> 5] = (uint32_t)__popc(mF);
 		__syncthreads();
@@ -141,16 +144,20 @@ __global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbSc
 			s_base = base;
 		}
 		__syncthreads();
-		if(state == ST_FETCH)
+		if(need)
 		{
 			const uint32_t j = s_base + before + (uint32_t)__popc(mF & ltMask);
 			if(j < totalItems)
 			{
 				item = j;
 				start = flat_setup_voxel(S, T, requests, numRequests, firstCta, ctaStride, j, L, state);
+				need = !start;
 			}
 			else
+			{
 				state = ST_DONE;
+				need = false;
+			}
 		}
 		__syncthreads(); /* s_warpCount / s_base are rewritten by the next round */
 	}

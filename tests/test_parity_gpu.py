@@ -487,9 +487,24 @@ def test_lighting_checkpoint_round_trip(dn, tmp_path):
         e.close()
 
 
+def _poison_staging(dn, e):
+    """fills the staging array with 0xAB bytes (through torch: the library has no reason to offer this)"""
+    import torch
+    from doonengine_b200.multigpu import _DevicePtr
+    L = dn.lib()
+    e.synchronize()
+    ptr, nbytes = L.DN_b200_array_device_ptr(e.vol, dn.ARRAY_STAGING), L.DN_b200_array_bytes(e.vol, dn.ARRAY_STAGING)
+    if ptr and nbytes:
+        torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda").fill_(0xAB)
+        torch.cuda.synchronize()
+
+
 def test_kernels_agree_on_sparse_map_with_streamed_pool(dn, light_kernel):
     """the three lighting kernels stage the same words on a sparse map (long rays of very different length, glossy and emissive balls),
     with the wavefront context pool far smaller than the dispatch so that slots are refilled pass after pass, and at several pool sizes.
+    The staging array is POISONED before every kernel's run: a kernel that skips work items (round 1's persistent and wavefront
+    kernels dropped every item a lane fetched while still holding a freshly fetched one -- invisible while the previous kernel's
+    identical words were still lying in the rows) leaves the poison behind.
     Runs once (under the "warp" parametrisation): it drives all kernels itself."""
     if light_kernel != "warp":
         pytest.skip("drives every kernel itself")
@@ -506,12 +521,16 @@ def test_kernels_agree_on_sparse_map_with_streamed_pool(dn, light_kernel):
             n = e.num_requests()
             assert n > 2000
             staged = {}
+            L.DN_b200_set_light_kernel(0)
+            assert L.DN_b200_light_compute(e.vol, 1, 1000, 1.0 + k / 60.0)  # sizes the staging array for this frame's request count
             for name, mode, slots in (("warp", 0, 0), ("flat", 1, 0), ("wave-all", 3, 1 << 22), ("wave-4k", 3, 4096), ("wave-640", 3, 640)):
                 L.DN_b200_set_light_kernel(mode)
                 if mode == 3:
                     L.DN_b200_set_wave_slots(slots)
+                _poison_staging(dn, e)
                 assert L.DN_b200_light_compute(e.vol, 1, 1000, 1.0 + k / 60.0)
                 staged[name] = e.download(dn.ARRAY_STAGING, np.uint32)[:n * 96].copy()
+                assert not (staged[name] == 0xABABABAB).any(), "frame %d: %s left %d staging words unwritten" % (k, name, int((staged[name] == 0xABABABAB).sum()))
             for name, words in staged.items():
                 assert np.array_equal(words, staged["warp"]), "frame %d: %s differs from the warp-per-request kernel in %d words" % (k, name, int((words != staged["warp"]).sum()))
             assert staged["warp"].any()
