@@ -110,7 +110,7 @@ bool device_create(VolumeImpl* v)
 	const uint32_t cb = dnb_compact_num_blocks((uint32_t)tiles);
 	ok = ok && device_reserve(v->blockCounts, cb ? cb : 1, false, true, "compaction counts");
 	ok = ok && device_reserve(v->blockOffsets, cb ? cb : 1, false, true, "compaction offsets");
-	ok = ok && device_reserve(v->scalars, 16, false, true, "scalars");
+	ok = ok && device_reserve(v->scalars, 32, false, true, "scalars");
 	ok = ok && device_reserve(v->litCounter, 1, false, true, "lit counter");
 	if(ok && !v->pinnedScalars)
 		ok = cuda_ok(cudaMallocHost((void**)&v->pinnedScalars, 16 * sizeof(uint32_t)), "pinned scalars");
@@ -1530,7 +1530,7 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	{
 		const uint32_t P = wave_pool_slots(numCtas);
 		ok = ok && (P == 0 || device_reserve(v->waveCtx, (size_t)P * (dnb_wave_slot_bytes() / sizeof(uint4)), false, false, "wavefront lighting contexts"));
-		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 12, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
+		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 16, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
 	}
 	else
 		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");

@@ -278,7 +278,19 @@ void fgl_collect_uniforms(int program, OrbUniforms* u)
 }
 
 /* ------------------------------------------------------------------ */
-/* dispatch = run Oracle B                                              */
+/* dispatch = run Oracle B, or -- after fgl_set_device -- whatever the harness plugged in: oracle/_ref/libglsl_ref.so's glsl_draw /
+ * glsl_light, i.e. the reference's OWN shaders compiled as C++; together with this file's host that is the complete reference
+ * pipeline, both halves unrestated (tests/golden/make_golden.py generates the fixtures that way) */
+typedef void (*FglDrawFn)(const OrbBuffers*, const OrbUniforms*, int, int, float*, OrbHit*);
+typedef void (*FglLightFn)(const OrbBuffers*, const OrbUniforms*, const uint32_t*, size_t, size_t);
+static FglDrawFn  g_deviceDraw = NULL;
+static FglLightFn g_deviceLight = NULL;
+
+void fgl_set_device(void* drawFn, void* lightFn)
+{
+	g_deviceDraw = (FglDrawFn)drawFn;
+	g_deviceLight = (FglLightFn)lightFn;
+}
 
 static void APIENTRY fgl_DispatchCompute(GLuint x, GLuint y, GLuint z)
 {
@@ -301,13 +313,21 @@ static void APIENTRY fgl_DispatchCompute(GLuint x, GLuint y, GLuint z)
 	if(p == FGL_PROGRAM_LIGHTING)
 	{
 		const uint32_t* requests = (const uint32_t*)g_buffers[g_bindingBase[3]].data;
-		orb_light(&b, &u, requests, x, g_buffers[g_bindingBase[4]].size / sizeof(OrbVoxel), &g_counters[p]);
+		if(g_deviceLight)
+			g_deviceLight(&b, &u, requests, x, g_buffers[g_bindingBase[4]].size / sizeof(OrbVoxel));
+		else
+			orb_light(&b, &u, requests, x, g_buffers[g_bindingBase[4]].size / sizeof(OrbVoxel), &g_counters[p]);
 	}
 	else
 	{
 		FglTexture* t = &g_textures[g_imageTexture];
 		if(g_imageTexture > 0 && g_imageTexture < FGL_MAX_TEXTURES && t->used)
-			orb_draw(&b, &u, t->w, t->h, t->pixels, t->hits, &g_counters[p]);
+		{
+			if(g_deviceDraw)
+				g_deviceDraw(&b, &u, t->w, t->h, t->pixels, t->hits);
+			else
+				orb_draw(&b, &u, t->w, t->h, t->pixels, t->hits, &g_counters[p]);
+		}
 	}
 }
 

@@ -87,7 +87,7 @@ assert C.sizeof(DNvolume) == 232
 
 def build(force=False):
     """compile liboracle.so and (when /root/reference exists) _ref/libdoon_ref.so."""
-    if force or not os.path.exists(LIB_ORACLE) or (os.path.isdir("/root/reference") and not os.path.exists(LIB_REF)):
+    if force or not os.path.exists(LIB_ORACLE) or (os.path.isdir("/root/reference") and not (os.path.exists(LIB_REF) and os.path.exists(os.path.join(HERE, "_ref", "libglsl_ref.so")))):
         subprocess.check_call(["make", "-s", "-C", HERE] + (["-B"] if force else []))
     return LIB_ORACLE
 
@@ -310,13 +310,63 @@ class OracleEngine(_EngineBase):
         return int(self.L.orb_num_threads())
 
 
+LIB_GLSL = os.path.join(HERE, "_ref", "libglsl_ref.so")
+
+
+def have_glsl():
+    return os.path.exists(LIB_GLSL)
+
+
+class OrbBuffers(C.Structure):
+    _fields_ = [("map", C.c_void_p), ("chunks", C.c_void_p), ("voxels", C.c_void_p), ("materials", C.c_void_p)]
+
+
+class GlslEngine(OracleEngine):
+    """the restated host (host_cpu.c) with the reference's OWN shaders as its device: every dispatch runs the text of
+    assets/shaders/voxel{Shared,Lighting,Draw}.comp compiled as C++ (oracle/glsl/, oracle/_ref/libglsl_ref.so) instead of the hand
+    restatement shader_cpu.c.  Exists only where /root/reference does; used to PIN shader_cpu.c (tests/test_glsl_pin.py)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        if not have_glsl():
+            build()
+        if not have_glsl():
+            raise RuntimeError("oracle/_ref/libglsl_ref.so is not built and /root/reference is absent")
+        G = C.CDLL(LIB_GLSL)
+        G.glsl_draw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        G.glsl_light.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+        self.G = G
+
+    def _buffers(self):
+        L = self.L
+        return OrbBuffers(L.orh_map(self.v), L.orh_gpu_chunks(self.v), L.orh_voxels(self.v), L.orh_materials(self.v))
+
+    def draw(self, w, h, aspect=None, want_hits=False):
+        view, proj = self.view_projection(aspect if aspect is not None else h / w)
+        u = OrbUniforms()
+        self.L.orh_draw_uniforms(self.v, view.ctypes.data, proj.ctypes.data, C.byref(u))
+        img = np.zeros((h, w, 4), np.float32)
+        hits = np.zeros((h, w), HIT_DT) if want_hits else None
+        buf = self._buffers()
+        self.G.glsl_draw(C.byref(buf), C.byref(u), w, h, img.ctypes.data, hits.ctypes.data if want_hits else None)
+        return (img, hits) if want_hits else img
+
+    def update_lighting(self, num_diffuse=1, max_diffuse=1000, time=1.0):
+        u = OrbUniforms()
+        self.L.orh_light_uniforms(self.v, num_diffuse, max_diffuse, C.c_float(time), C.byref(u))
+        buf = self._buffers()
+        self.G.glsl_light(C.byref(buf), C.byref(u), self.L.orh_requests(self.v), self.L.orh_num_requests(self.v), self.L.orh_voxel_top(self.v))
+
+
 _MSG_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_char_p)
 
 
 class RefEngine(_EngineBase):
     """the reference's own host code (voxel.c) with Oracle B as its GPU."""
 
-    def __init__(self, map_size=None, min_chunks=256, voxvol=None, resident=True):
+    def __init__(self, map_size=None, min_chunks=256, voxvol=None, resident=True, glsl=False):
+        """glsl=True: the dispatches run the reference's own shaders (oracle/_ref/libglsl_ref.so) instead of the restatement --
+        reference host + reference shaders, nothing restated."""
         if not have_ref():
             build()
         if not have_ref():
@@ -369,6 +419,14 @@ class RefEngine(_EngineBase):
         L.fgl_upload_bytes.restype = C.c_size_t
         L.fgl_binding.restype = C.c_uint
         L.fgl_binding.argtypes = [C.c_uint]
+        L.fgl_set_device.argtypes = [C.c_void_p, C.c_void_p]
+        if glsl:
+            if not have_glsl():
+                raise RuntimeError("oracle/_ref/libglsl_ref.so is not built")
+            self.G = C.CDLL(LIB_GLSL)
+            L.fgl_set_device(C.cast(self.G.glsl_draw, C.c_void_p), C.cast(self.G.glsl_light, C.c_void_p))
+        else:
+            L.fgl_set_device(None, None)
         if not L.DN_init():
             raise RuntimeError("reference DN_init failed under the shim")
         if voxvol is not None:
