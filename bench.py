@@ -447,7 +447,7 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         for key, dt in (("edits", t1 - t0), ("draw", t2 - t1), ("read_back_enqueue", t3 - t2), ("sync", t4 - t3), ("light_compute", t5 - t4), ("commit", t6 - t5), ("wait_read", t7 - t6)):
             host_s[key] += dt
         host_s["steps"] += 1
-        return marks, int(e.vol.contents.numLightingRequests)
+        return marks, 0  # (the request count stays on the device: it is asked for once, after the loop)
 
     def barrier():
         if world > 1:
@@ -478,6 +478,7 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         drain1.record(stream)
         barrier()
         wall = time.perf_counter() - wall0
+        reqs = steps * e.num_requests()  # the request count stays on the device during the frame calls; asked for here, after the region (static camera: the same list every step)
         clocks = sampler.finish() if args.sampler_ms > 0 else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         phases = np.zeros(5)
         for m in all_marks:
@@ -539,7 +540,7 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
     else:
         sh.draw(fbs[0], view, proj)
     L.DN_sync_gpu(e.vol, dn.DN_READ_WRITE, 1)
-    r_count = int(e.vol.contents.numLightingRequests)
+    r_count = e.num_requests()
     sh.light_compute(1, 1000, frame_time(warmup + 2 * steps))
     if rank == 0:
         cl = e.counters(reset=True)

@@ -188,6 +188,9 @@ _PROTOTYPES = {
     "DN_b200_rescan": (None, [C.POINTER(DNvolume)]),
     "DN_b200_pack_chunk": (C.c_int, [C.POINTER(DNvolume), DNivec3, C.c_void_p, C.c_void_p]),
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
+    "DN_b200_lighting_request_count": (C.c_size_t, [C.POINTER(DNvolume)]),
+    "DN_b200_set_exact_sync": (None, [C.POINTER(DNvolume), C.c_bool]),
+    "DN_b200_mirror_voxel_layout": (C.c_bool, [C.POINTER(DNvolume)]),
     "DN_b200_step_map_batch": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "DN_b200_set_wave_slots": (None, [C.c_uint32]),
     "DN_b200_set_chunks": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
@@ -500,7 +503,8 @@ class Engine:
         return _view(self.vol.contents.lightingRequests, np.dtype("<u4"), n).copy()
 
     def num_requests(self):
-        return int(self.vol.contents.numLightingRequests)
+        """exact length of the request list of the last reading sync (waits for the device if it is still in flight)"""
+        return int(self.L.DN_b200_lighting_request_count(self.vol))
 
     def export_state(self):
         """dict mapIndex -> (state, visible, header(pos, samples, partialCounts, bitMask), records[n,4]) in the same

@@ -826,14 +826,15 @@ static void sync_read(VolumeImpl* v, uint32_t split)
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_NOTE, "automatically resizing lighting request buffer to accomodate %zu requests (%zu bytes)", cap, cap * sizeof(uint32_t));
 		device_reserve(v->requests, cap, false, false, "lighting requests");
 	}
-	/* the count kernel stores the total straight into the pinned host word; the host waits for THAT kernel only (an event), not for
-	 * a copy-engine transfer that would queue behind a framebuffer read-back, and not for the write pass */
+	/* the count kernel leaves the total in a device word (read there by the lighting and commit kernels) and also stores it straight
+	 * into a pinned host word; nobody waits for it here: the host sizes everything from the bound it knows, and reads the exact
+	 * number only when somebody asks (request_count) */
 	Context& cx = ctx();
 	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, v->pinnedScalars, s), "compaction count");
 	cuda_ok(cudaEventRecord(cx.evCountDone, s), "event record");
 	cuda_ok(dnb_launch_compact_write(&scene, forced, split, vol->frameNum, v->blockOffsets.ptr, v->requests.ptr, s), "compaction write");
-	cuda_ok(cudaEventSynchronize(cx.evCountDone), "compaction");
-	const size_t total = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars);
+	v->requestBound = v->residentGroups;
+	v->countPending = true;
 
 	if(forced)
 	{
@@ -842,8 +843,30 @@ static void sync_read(VolumeImpl* v, uint32_t split)
 		v->forcedDirty = false;
 	}
 
-	vol->numLightingRequests = total;
-	v->requestsValid = total;
+	/* numLightingRequests: exact at return if the application asked for upstream's semantics (DN_b200_set_exact_sync) or the device
+	 * happens to be done already; otherwise it keeps the last exact value until DN_b200_lighting_request_count / _fetch_ is called */
+	request_count(v, v->exactSync);
+}
+
+size_t request_count(VolumeImpl* v, bool wait)
+{
+	if(v->countPending)
+	{
+		Context& cx = ctx();
+		cudaError_t q = wait ? cudaEventSynchronize(cx.evCountDone) : cudaEventQuery(cx.evCountDone);
+		if(q == cudaSuccess)
+		{
+			v->requestsValid = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars);
+			v->lastExactCount = v->requestsValid;
+			v->pub.numLightingRequests = v->requestsValid;
+			v->countPending = false;
+		}
+		else if(q != cudaErrorNotReady)
+			cuda_ok(q, "request count");
+		else
+			cudaGetLastError(); /* not ready is not an error */
+	}
+	return v->countPending ? v->lastExactCount : v->requestsValid;
 }
 
 } // namespace dnb
@@ -1208,12 +1231,18 @@ extern "C" void DN_sync_gpu(DNvolume* vol, DNmemOp op, int lightingSplit)
 	vol->frameNum++;
 	if(vol->frameNum >= (uint32_t)lightingSplit)
 		vol->frameNum = 0;
-	vol->numLightingRequests = 0;
-	v->requestsValid = 0;
-
 	/* requests first: they are sized from what is resident BEFORE this call's uploads (voxel.c:757 precedes :761) */
 	if(op != DN_WRITE)
 		sync_read(v, (uint32_t)lightingSplit);
+	else
+	{
+		/* a sync that does not read leaves an empty request list (voxel.c:729: numLightingRequests = 0) */
+		vol->numLightingRequests = 0;
+		v->requestsValid = 0;
+		v->requestBound = 0;
+		v->countPending = false;
+		cuda_ok(cudaMemsetAsync(v->scalars.ptr, 0, sizeof(uint32_t), ctx().stream()), "request count clear");
+	}
 	if(op != DN_READ)
 		sync_write(v);
 }
@@ -1415,10 +1444,20 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	if(vol->frameNum == 0)
 		vol->lastTime = time;
 
-	const size_t total = v->requestsValid;
-	v->stagedRequests = total;
+	/* the list's length stays on the device; the host works from the bound it knows (engine.h).  Only the host-driven sharding
+	 * (contiguous slices exchanged with all-gathers) needs the exact number: its slice boundaries are derived from it. */
+	const bool needExact = v->shardWorld > 1 && !v->peerAttached;
+	const size_t bound = v->requestBound;
+	const size_t total = needExact ? request_count(v, true) : bound;
+	v->stagedRequests = needExact ? total : 0;
+	v->stagedBound = bound;
 	if(total == 0 && !v->peerAttached)
 		return true; /* (attached replicas still fence and clear their propagate bitmap below) */
+	/* grids are sized from the last exact count the host has seen (it lags a frame behind), with slack; the kernels stride or pull
+	 * work from counters, so any size is correct */
+	request_count(v, v->lastExactCount == 0); /* (the very first dispatches have nothing to go by: wait once) */
+	const size_t seen = v->countPending ? v->lastExactCount + v->lastExactCount / 4 + 1024 : v->requestsValid;
+	const size_t expect = std::max<size_t>(std::min<size_t>(seen, bound), 1);
 
 	if(numDiffuseSamples < 0) numDiffuseSamples = 0;
 	if(numDiffuseSamples > DNB_MAX_SAMPLES || vol->diffuseBounceLimit > DNB_MAX_BOUNCES)
@@ -1458,8 +1497,12 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	fill_scene(v, &scene);
 
 	/* the CTAs (4 requests each) this process lights, and where their staged words go */
-	const uint32_t totalCtas = (uint32_t)((total + 3) / 4);
+	const uint32_t totalCtas = (uint32_t)(((needExact ? total : expect) + 3) / 4);
 	uint32_t firstCta = 0, ctaStride = 1, numCtas = totalCtas;
+	DnbWork work;
+	memset(&work, 0, sizeof(work));
+	work.count = needExact ? nullptr : v->scalars.ptr;
+	work.ctaStride = 1;
 	DnbStagingTargets targets;
 	memset(&targets, 0, sizeof(targets));
 	if(v->peerAttached)
@@ -1475,6 +1518,8 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 		firstCta = (uint32_t)v->shardRank;
 		ctaStride = (uint32_t)v->shardWorld;
 		numCtas = totalCtas > firstCta ? (totalCtas - firstCta + ctaStride - 1) / ctaStride : 0;
+		work.firstCta = firstCta;
+		work.ctaStride = ctaStride;
 		targets.count = v->peers.world;
 		for(uint32_t p = 0; p < v->peers.world; p++)
 			targets.dst[p] = v->peers.staging[p];
@@ -1496,6 +1541,10 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 			paddedTotal = per * (size_t)v->shardWorld;
 			firstCta = (uint32_t)(first / 4);
 			numCtas = (uint32_t)((count + 3) / 4);
+			/* a slice that is not the last one ends on a CTA boundary (slice_len is a multiple of 4); the last CTA of the list is cut by the limit */
+			work.limit = (uint32_t)std::min(total, per * (size_t)(v->shardRank + 1));
+			work.firstCta = firstCta;
+			work.numCtas = numCtas;
 		}
 		/* grown with half as much again in reserve: the request count creeps up frame by frame while a map is being edited, and
 		 * every reallocation synchronises the device (config 4: a cudaMalloc + cudaFree per frame showed up as 6 ms of "lighting") */
@@ -1511,8 +1560,6 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	ScopedTimer timer(&v->stats.lastLightMs, s);
 	bool ok = sync_materials(v, s);
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
-	/* a slice that is not the last one ends on a CTA boundary (slice_len is a multiple of 4); the last CTA of the list is cut by numRequests */
-	const uint32_t limit = v->peerAttached || v->shardWorld == 1 ? (uint32_t)total : (uint32_t)std::min(total, slice_len(total, v->shardWorld) * (size_t)(v->shardRank + 1));
 	int timingSlot = -1;
 	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
 	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself, and so does the persistent kernel
@@ -1530,12 +1577,12 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	{
 		const uint32_t P = wave_pool_slots(numCtas);
 		ok = ok && (P == 0 || device_reserve(v->waveCtx, (size_t)P * (dnb_wave_slot_bytes() / sizeof(uint4)), false, false, "wavefront lighting contexts"));
-		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 16, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
+		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, &work, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 16, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
 	}
 	else
-		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, limit, firstCta, ctaStride, numCtas, &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
+		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, &work, std::max<uint32_t>(numCtas, 1u), &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
 	if(pushAfter)
-		ok = ok && cuda_ok(dnb_launch_push_staging(&allPeers, v->peers.rank, firstCta, ctaStride, numCtas, limit, s), "staging push");
+		ok = ok && cuda_ok(dnb_launch_push_staging(&allPeers, v->peers.rank, &work, std::max<uint32_t>(numCtas, 1u), s), "staging push");
 	if(timingSlot >= 0)
 		cudaEventRecord(v->tuner.end[timingSlot], s);
 	v->tuner.launches[kernel]++;
@@ -1552,7 +1599,13 @@ static bool light_commit(VolumeImpl* v)
 	ScopedTimer timer(&v->stats.lastCommitMs, s);
 	if(v->peerAttached && v->peerMode == DN_B200_PEER_AUTO)
 		peer_barrier(v); /* every replica has stored its staged words into this replica's staging array */
-	const bool ok = cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, (uint32_t)v->stagedRequests, v->staging.ptr, v->litCounter.ptr,
+	/* every replica commits the WHOLE list from its own staging array; the length is read on the device */
+	DnbWork work;
+	memset(&work, 0, sizeof(work));
+	work.count = v->scalars.ptr;
+	work.ctaStride = 1;
+	const size_t seen = v->countPending ? std::min<size_t>(v->lastExactCount + v->lastExactCount / 4 + 1024, v->stagedBound) : std::min(v->requestsValid, v->stagedBound);
+	const bool ok = cuda_ok(dnb_launch_commit(&scene, v->slots.ptr, v->records.ptr, v->requests.ptr, &work, (uint32_t)(v->stagedBound ? std::max<size_t>(seen, 1) : 0), v->staging.ptr, v->litCounter.ptr,
 	                                          v->peerAttached ? &v->peers : nullptr, s), "commit kernel");
 	v->peerFenceSinceCommit = false;
 	return ok;
@@ -1629,12 +1682,12 @@ static bool array_info(VolumeImpl* v, DNb200array which, void** ptr, size_t* byt
 	case DN_B200_VISIBLE:    *ptr = v->visible.ptr;  *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
 	case DN_B200_SLOTS:      *ptr = v->slots.ptr;    *bytes = (size_t)v->slotTop * sizeof(DnbSlot); return true;
 	case DN_B200_RECORDS:    *ptr = v->records.ptr;  *bytes = v->pool.top * sizeof(uint4); return true;
-	case DN_B200_REQUESTS:   *ptr = v->requests.ptr; *bytes = v->requestsValid * sizeof(uint32_t); return true;
+	case DN_B200_REQUESTS:   *ptr = v->requests.ptr; *bytes = request_count(v, true) * sizeof(uint32_t); return true;
 	case DN_B200_PROPAGATE:  *ptr = v->propagate.ptr; *bytes = ((tiles + 31) / 32) * sizeof(uint32_t); return true;
 	case DN_B200_STAGING:
 	{
 		*ptr = v->staging.ptr;
-		*bytes = (v->peerAttached || v->shardWorld <= 1 ? v->stagedRequests : slice_len(v->stagedRequests, v->shardWorld) * v->shardWorld) * 96 * sizeof(uint32_t);
+		*bytes = (v->peerAttached || v->shardWorld <= 1 ? std::min(request_count(v, true), v->stagedBound) : slice_len(v->stagedRequests, v->shardWorld) * v->shardWorld) * 96 * sizeof(uint32_t);
 		return true;
 	}
 	}
@@ -1673,7 +1726,7 @@ extern "C" size_t DN_b200_download(DNvolume* vol, DNb200array which, void* dst, 
 extern "C" size_t DN_b200_fetch_lighting_requests(DNvolume* vol)
 {
 	VolumeImpl* v = impl_of(vol);
-	const size_t total = v->requestsValid;
+	const size_t total = request_count(v, true);
 	if(total > vol->lightingRequestCap)
 	{
 		size_t cap = vol->lightingRequestCap ? vol->lightingRequestCap : 1;
@@ -1685,6 +1738,20 @@ extern "C" size_t DN_b200_fetch_lighting_requests(DNvolume* vol)
 	if(total && DN_b200_download(vol, DN_B200_REQUESTS, vol->lightingRequests, vol->lightingRequestCap * sizeof(GLuint)) == 0)
 		return 0;
 	return total;
+}
+
+/* the exact length of the request list of the last reading DN_sync_gpu (waits for the device if it is still in flight) */
+extern "C" size_t DN_b200_lighting_request_count(DNvolume* vol)
+{
+	VolumeImpl* v = impl_of(vol);
+	if(!ctx().ready)
+		return 0;
+	return request_count(v, true);
+}
+
+extern "C" void DN_b200_set_exact_sync(DNvolume* vol, bool exact)
+{
+	impl_of(vol)->exactSync = exact;
 }
 
 extern "C" bool DN_b200_enable_counters(DNvolume* vol, bool enable)
@@ -1929,7 +1996,7 @@ extern "C" void DN_b200_peer_detach(DNvolume* vol)
 extern "C" bool DN_b200_peer_capacity_ok(DNvolume* vol)
 {
 	VolumeImpl* v = impl_of(vol);
-	return !v->peerAttached || v->requestsValid <= v->peerRequestCap;
+	return !v->peerAttached || v->requestBound <= v->peerRequestCap;
 }
 
 extern "C" bool DN_b200_framebuffer_set_mirror(GLuint id, void* mirrorImage)

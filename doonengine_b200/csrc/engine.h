@@ -98,8 +98,15 @@ struct VolumeImpl
 	uint32_t       opaqueBits[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* materials with opacity == 1.0 in the table the slots' DNB_BBOX_OPAQUE flags were derived from */
 	bool           opaqueBitsValid = false;
 
-	size_t requestsValid = 0;                  /* requests on the device from the last reading sync */
-	size_t stagedRequests = 0;                 /* requests covered by the staging array (last compute phase) */
+	/* ---- the lighting-request list of the last reading sync.  Its length stays on the device (scalars[0], read there by the lighting
+	 * and commit kernels: layout.h DnbWork); the host knows an upper bound at once and the exact number when it asks (request_count) ---- */
+	size_t requestBound = 0;                   /* the list cannot be longer than this: the 32-voxel groups of everything resident at that sync */
+	bool   countPending = false;               /* the exact length has not been read back yet (evCountDone / pinnedScalars[0]) */
+	size_t requestsValid = 0;                  /* exact length, once known (0 after a sync that did not read) */
+	size_t lastExactCount = 0;                 /* the most recent exact length seen: sizes grids while the current one is still in flight */
+	bool   exactSync = false;                  /* DN_sync_gpu waits for the exact length (numLightingRequests valid at return, as upstream) */
+	size_t stagedBound = 0;                    /* requestBound of the last compute phase (sizes the staging array and the commit grid) */
+	size_t stagedRequests = 0;                 /* exact length used by the last compute phase, where it was needed (collective sharding), else 0 */
 	int    shardRank = 0, shardWorld = 1;
 
 	/* ---- lighting-kernel selection (engine.cpp pick_light_kernel): both kernels give the same bits, so the faster one for
@@ -144,6 +151,7 @@ bool device_create(VolumeImpl* v);   /* allocates the per-tile arrays for pub.ma
 void device_destroy(VolumeImpl* v);
 void fill_scene(VolumeImpl* v, DnbScene* s);
 bool sync_materials(VolumeImpl* v, cudaStream_t s);
+size_t request_count(VolumeImpl* v, bool wait); /* exact length of the current request list; !wait: the last known one if it is still in flight */
 
 } // namespace dnb
 

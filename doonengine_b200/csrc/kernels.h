@@ -26,23 +26,25 @@ extern unsigned long long g_dnbKernelLaunches;
 cudaError_t dnb_launch_draw(const DnbScene* scene, const DnbDrawParams* params, float4* image, float4* mirror, DnbHit* hits, cudaStream_t stream);
 
 cudaError_t dnb_upload_light_params(const DnbLightParams* params, cudaStream_t stream);
-/* lights the 4-request CTAs  firstCta, firstCta + ctaStride, ...  of requests[0, numRequests) and stores the staged words of
- * request r at word 96 r of every array in `targets`.
+/* lights this launch's share of the request list (DnbWork, layout.h: the count is read on the device) and stores the staged words of
+ * request r at word 96 r of every array in `targets`.  gridCtas: CTAs to launch (the warp-per-request kernel strides over its share,
+ * so any number >= 1 is correct) / the ceiling of the persistent kernel's grid.
  * flatCounter: NULL = dn_light_kernel (one warp per request); else a device word used as the work counter of the persistent
  * state-machine kernel dn_light_flat_kernel (light_flat.cuh).  Both give identical results. */
-cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, const DnbWork* work, uint32_t gridCtas,
                              const DnbStagingTargets* targets, uint32_t* flatCounter, cudaStream_t stream);
 /* the same dispatch as a wavefront over a pool of P context slots in global memory (light_wave.cuh): ctx = dnb_wave_slot_bytes() * P
- * bytes, P a multiple of 128; counters = 4 device words.  Queues its passes on `stream` and returns once the last voxel is staged
+ * bytes, P a multiple of 256; counters = 8 device words.  Queues its passes on `stream` and returns once the last voxel is staged
  * (the host follows the live-slot count a few passes behind); passesOut = passes queued. */
 size_t      dnb_wave_slot_bytes(void);
-cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, const DnbWork* work,
                                   const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream);
-/* copies the staged rows of the CTAs firstCta, firstCta + ctaStride, ... from replica `self`'s staging array (peers->dst[self]) into every
- * other replica's (coalesced 16-byte stores over NVLink); used after the persistent / wavefront kernels, which stage locally */
-cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests, cudaStream_t stream);
-/* peers: NULL, or the table whose propagate bitmaps (all replicas') are ORed into visible instead of only the local one */
-cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
+/* copies the staged rows of this launch's CTAs from replica `self`'s staging array (peers->dst[self]) into every other replica's
+ * (coalesced 16-byte stores over NVLink); used after the wavefront kernels, which stage locally */
+cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, uint32_t self, const DnbWork* work, uint32_t gridCtas, cudaStream_t stream);
+/* peers: NULL, or the table whose propagate bitmaps (all replicas') are ORed into visible instead of only the local one.
+ * boundRequests: what the host knows the request count cannot exceed (sizes the persistent grid; 0 = no requests) */
+cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, const DnbWork* work, uint32_t boundRequests, const uint32_t* staging,
                               unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream);
 
 /* pick.cu: `count` DN_step_map rays (voxel.c:1195-1272) on the device map; out[i] = {cell, code} (see dn_pick_kernel) */

@@ -140,6 +140,17 @@ typedef struct DnbStagingTargets
 	uint32_t* dst[DNB_MAX_PEERS];
 } DnbStagingTargets;
 
+/* which lighting requests a launch covers.  The request COUNT normally stays on the device: the compaction kernels leave it in a
+ * device word and the lighting / commit kernels read it there, so DN_sync_gpu need not wait for it (the host only knows an upper
+ * bound -- the groups of everything resident -- and sizes buffers and grids from that and from the last count it has seen). */
+typedef struct DnbWork
+{
+	const uint32_t* count;    /* device word holding the length of the request list, or NULL: `limit` is the length */
+	uint32_t limit;           /* count == NULL: the length; else, if non-zero, an upper clamp (requests [0, limit) only) */
+	uint32_t firstCta, ctaStride; /* the launch handles the 4-request CTAs firstCta, firstCta + ctaStride, ... */
+	uint32_t numCtas;         /* how many of them; 0 = as many as the request count gives */
+} DnbWork;
+
 /* random numbers of one lighting dispatch.  Every seed in voxelLighting.comp is a function of
  * (time, sample, bounce) only, never of the voxel (LI:75,162-168,259-260), so the host evaluates
  * rand()/rand_unit_sphere() once per dispatch with libm sinf and every thread reads the same table. */

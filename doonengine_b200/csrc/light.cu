@@ -225,18 +225,48 @@ DNB_FN void stage_words(const DnbStagingTargets& T, size_t at, uint32_t w1, uint
 		}
 }
 
+/* the request count and this launch's share of the 4-request CTAs (layout.h DnbWork) */
+DNB_FN uint32_t work_requests(const DnbWork& W)
+{
+	if(!W.count)
+		return W.limit;
+	const uint32_t n = *reinterpret_cast<const volatile uint32_t*>(W.count);
+	return (W.limit && n > W.limit) ? W.limit : n;
+}
+DNB_FN uint32_t work_ctas(const DnbWork& W, uint32_t numRequests)
+{
+	if(W.numCtas)
+		return W.numCtas;
+	const uint32_t total = (numRequests + 3u) / 4u;
+	return total > W.firstCta ? (total - W.firstCta + W.ctaStride - 1u) / W.ctaStride : 0u;
+}
+
 /* registers: ptxas settles at 96 (5 CTAs = 20 warps per SM) with a few spills; both fewer registers (more warps, more spills) and
  * more registers (no spills, 16 warps) measured slower on B200 (0.49 / 0.54 ms vs 0.45 ms on config 2) */
 template <bool COUNT>
-__global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, DnbStagingTargets T)
+DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ requests, uint32_t r, uint32_t warp, uint32_t lane, const DnbStagingTargets& T, DnbSlot* s_slot);
+
+/* grid-stride over this launch's CTAs of 4 requests: the grid is sized from what the host knows (an upper bound and the last count it
+ * saw), the real count is read on the device */
+template <bool COUNT>
+__global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W, DnbStagingTargets T)
 {
 	__shared__ DnbSlot s_slot[4];
-
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t r = (firstCta + blockIdx.x * ctaStride) * 4 + warp;
-	if(r >= numRequests)
-		return;
+	const uint32_t numRequests = work_requests(W);
+	const uint32_t numCtas = work_ctas(W, numRequests);
+	for(uint32_t k = blockIdx.x; k < numCtas; k += gridDim.x)
+	{
+		const uint32_t r = (W.firstCta + k * W.ctaStride) * 4 + warp;
+		if(r < numRequests)
+			light_request<COUNT>(S, requests, r, warp, lane, T, s_slot);
+		__syncwarp();
+	}
+}
 
+template <bool COUNT>
+DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ requests, uint32_t r, uint32_t warp, uint32_t lane, const DnbStagingTargets& T, DnbSlot* s_slot)
+{
 	const uint32_t request = __ldg(requests + r);
 	const uint32_t mapIndex = request >> 4;
 	const size_t at = (size_t)r * 96u + lane;
@@ -343,11 +373,12 @@ __global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_
  * per CTA and added with ONE atomic per CTA: with one atomic per request the 10^7 same-address atomics of a full-size dispatch
  * WERE the kernel (11.4 ms for 10.9 M requests on B200, 1.2 TB/s; the streaming itself needs a quarter of that). */
 __global__ void __launch_bounds__(256) dn_commit_kernel(const uint32_t* __restrict__ tileSlot, DnbSlot* __restrict__ slots, uint4* __restrict__ records, uint32_t* __restrict__ visible,
-                                                        const uint32_t* __restrict__ requests, uint32_t numRequests, const uint32_t* __restrict__ staging,
+                                                        const uint32_t* __restrict__ requests, DnbWork W, const uint32_t* __restrict__ staging,
                                                         unsigned long long* __restrict__ litCounter)
 {
 	__shared__ uint32_t s_lit[8];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t numRequests = work_requests(W);
 	uint32_t lit = 0;
 	for(uint32_t r = blockIdx.x * 8 + warp; r < numRequests; r += gridDim.x * 8)
 	{
@@ -443,13 +474,15 @@ extern "C" cudaError_t dnb_upload_light_params(const DnbLightParams* params, cud
 	return cudaMemcpyToSymbolAsync(c_light, params, sizeof(DnbLightParams), 0, cudaMemcpyHostToDevice, stream);
 }
 
-extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+/* gridCtas: CTAs to launch for the warp-per-request kernel (any number >= 1 is correct: the kernel strides over its share) and the
+ * ceiling of the persistent kernel's grid */
+extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* requests, const DnbWork* work, uint32_t gridCtas,
                                         const DnbStagingTargets* targets, uint32_t* flatCounter, cudaStream_t stream)
 {
-	if(numRequests == 0 || numCtas == 0)
+	if(gridCtas == 0)
 		return cudaSuccess;
 	if(scene->counters)
-		{ DNB_LAUNCHED(1); dn_light_kernel<true><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets); }
+		{ DNB_LAUNCHED(1); dn_light_kernel<true><<<gridCtas, 128, 0, stream>>>(*scene, requests, *work, *targets); }
 	else if(flatCounter)
 	{
 		/* persistent warps: enough CTAs to fill the machine, each lane pulls voxels from the work counter */
@@ -466,7 +499,7 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 		cudaError_t e = cudaMemsetAsync(flatCounter, 0, sizeof(uint32_t), stream);
 		if(e != cudaSuccess)
 			return e;
-		const uint32_t grid = numCtas < (uint32_t)ctasPerDevice ? numCtas : (uint32_t)ctasPerDevice;
+		const uint32_t grid = gridCtas < (uint32_t)ctasPerDevice ? gridCtas : (uint32_t)ctasPerDevice;
 		DnbFlatTuning& tuning = g_flatTuning;
 		if(tuning.budget == 0)
 		{
@@ -475,10 +508,10 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 			tuning.endLanes = knob("DN_B200_FLAT_END", 28);
 			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 16);
 		}
-		{ DNB_LAUNCHED(1); dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, numCtas * 128u, flatCounter, *targets, tuning); }
+		{ DNB_LAUNCHED(1); dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, *work, flatCounter, *targets, tuning); }
 	}
 	else
-		{ DNB_LAUNCHED(1); dn_light_kernel<false><<<numCtas, 128, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, *targets); }
+		{ DNB_LAUNCHED(1); dn_light_kernel<false><<<gridCtas, 128, 0, stream>>>(*scene, requests, *work, *targets); }
 	return cudaGetLastError();
 }
 
@@ -487,11 +520,13 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
  * therefore stage into their own replica only, and this kernel then pushes the rows of the CTAs the replica owns (4 requests = 1536
  * contiguous bytes each) to the other replicas with coalesced 16-byte stores.  (The warp-per-request kernel keeps its fused 128-byte
  * row stores, and the persistent kernel its per-voxel stores, which overlap with its ray tracing.) */
-__global__ void __launch_bounds__(128) dn_push_staging_kernel(const uint4* __restrict__ own, DnbStagingTargets T, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests)
+__global__ void __launch_bounds__(128) dn_push_staging_kernel(const uint4* __restrict__ own, DnbStagingTargets T, uint32_t self, DnbWork W)
 {
+	const uint32_t numRequests = work_requests(W);
+	const uint32_t numCtas = work_ctas(W, numRequests);
 	for(uint32_t k = blockIdx.x; k < numCtas; k += gridDim.x)
 	{
-		const uint32_t cta = firstCta + k * ctaStride;
+		const uint32_t cta = W.firstCta + k * W.ctaStride;
 		const uint32_t firstRequest = cta * 4u;
 		if(firstRequest >= numRequests)
 			break;
@@ -508,18 +543,20 @@ __global__ void __launch_bounds__(128) dn_push_staging_kernel(const uint4* __res
 	}
 }
 
-extern "C" cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, uint32_t self, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas, uint32_t numRequests, cudaStream_t stream)
+extern "C" cudaError_t dnb_launch_push_staging(const DnbStagingTargets* peers, uint32_t self, const DnbWork* work, uint32_t gridCtas, cudaStream_t stream)
 {
-	if(numCtas == 0 || numRequests == 0 || peers->count < 2)
+	if(gridCtas == 0 || peers->count < 2)
 		return cudaSuccess;
-	const uint32_t grid = numCtas < 148u * 16u ? numCtas : 148u * 16u;
-	{ DNB_LAUNCHED(1); dn_push_staging_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(peers->dst[self]), *peers, self, firstCta, ctaStride, numCtas, numRequests); }
+	const uint32_t grid = gridCtas < 148u * 16u ? gridCtas : 148u * 16u;
+	{ DNB_LAUNCHED(1); dn_push_staging_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(peers->dst[self]), *peers, self, *work); }
 	return cudaGetLastError();
 }
 
-extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, uint32_t numRequests, const uint32_t* staging,
+/* boundRequests: what the host knows the request count cannot exceed (sizes the persistent grid; 0 = nothing to commit) */
+extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, uint4* records, const uint32_t* requests, const DnbWork* work, uint32_t boundRequests, const uint32_t* staging,
                                          unsigned long long* litCounter, const DnbPeerTable* peers, cudaStream_t stream)
 {
+	const uint32_t numRequests = boundRequests;
 	if(numRequests > 0)
 	{
 		/* persistent: 8 CTAs of 8 warps per SM at most (the kernel streams; its warps only wait on memory) */
@@ -532,7 +569,7 @@ extern "C" cudaError_t dnb_launch_commit(const DnbScene* scene, DnbSlot* slots, 
 			maxCtas = sms * 8;
 		}
 		const uint32_t ctas = std::min<uint32_t>((numRequests + 7) / 8, (uint32_t)maxCtas);
-		{ DNB_LAUNCHED(1); dn_commit_kernel<<<ctas, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, numRequests, staging, litCounter); }
+		{ DNB_LAUNCHED(1); dn_commit_kernel<<<ctas, 256, 0, stream>>>(scene->tileSlot, slots, records, scene->visible, requests, *work, staging, litCounter); }
 		cudaError_t e = cudaGetLastError();
 		if(e != cudaSuccess)
 			return e;

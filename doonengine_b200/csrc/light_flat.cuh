@@ -66,6 +66,7 @@ struct FlatLane
 	const DnbSlot* slot;
 	uint32_t wordIdx, word, cguard, mapIndex;
 	uint32_t cbias, coffp;   /* exact chunk cull (trace.cuh cull_offsets): cp is shifted by the offsets in coffp */
+	bool     chunkOpaque;    /* every material of the chunk is opaque (layout.h DNB_BBOX_OPAQUE): a set voxel bit is an opaque hit */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -145,12 +146,16 @@ DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 		L.cside = (t + 0.5f) * m.delta;
 		L.ctLast = 0.0f;
 		L.cguard = 0;
-		L.wordIdx = 0xFFFFFFFFu;
-		L.word = 0;
+		/* both loads that depend on the slot index leave together (the entry cell's mask word and the bounding-box word, whose top
+		 * bit says whether every material of the chunk is opaque: trace.cuh) */
+		L.wordIdx = ((uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z)) >> 5;
+		L.word = __ldg(L.slot->mask + L.wordIdx);
+		const uint32_t bbox = __ldg(&L.slot->bbox);
+		L.chunkOpaque = (bbox & DNB_BBOX_OPAQUE) != 0u;
 		L.cbias = 0;
 		L.coffp = 0;
 		if(L.st.lastVoxID == 255u)
-			L.coffp = cull_offsets(__ldg(&L.slot->bbox), m.step, L.cp, L.cbias);
+			L.coffp = cull_offsets(bbox, m.step, L.cp, L.cbias);
 		state = ST_VOX;
 		return;
 	}
@@ -188,7 +193,10 @@ DNB_FN void flat_vox_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 		const uint32_t rel = (uint32_t)__ldg(L.slot->prefix + L.wordIdx) + __popc(L.word & ((1u << (local & 31u)) - 1u));
 		const uint4 rec = __ldg(S.records + (__ldg(&L.slot->voxelBase) + rel));
 		L.st.vox = rec;
-		const DnbMaterial material = load_material(S, rec.x >> 24);
+		DnbMaterial material;
+		material.opacity = 1.0f;
+		if(!L.chunkOpaque)
+			material = load_material(S, rec.x >> 24);
 		const uint32_t thisVoxID = (rec.y & 0xFFFFFF00u) | (rec.x >> 24);
 
 		if(material.opacity == 1.0f)
@@ -530,9 +538,13 @@ DNB_FN bool flat_setup_voxel(const DnbScene& S, const DnbStagingTargets& T, cons
 #ifndef FLAT_MIN_BLOCKS
 #define FLAT_MIN_BLOCKS 5
 #endif
-__global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_flat_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
+__global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_flat_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W,
                                                                         uint32_t* __restrict__ workCounter, DnbStagingTargets T, DnbFlatTuning K)
 {
+	/* the request count is read on the device (layout.h DnbWork); a work item = one lane of a request */
+	const uint32_t numRequests = work_requests(W);
+	const uint32_t firstCta = W.firstCta, ctaStride = W.ctaStride;
+	const uint32_t totalItems = work_ctas(W, numRequests) * 128u;
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t ltMask = (1u << lane) - 1u;
 	FlatLane L;

@@ -60,9 +60,13 @@ DNB_FN f3 xyz_of(uint4 v) { return mk3(__uint_as_float(v.x), __uint_as_float(v.y
 /* pass: parity selects the counters / entry list written (pass & 1) and read (the other one).  drain != 0: the work counter is
  * exhausted -- only the slots of the previous pass's live entries are visited (warp w of the grid takes entry w) and nothing is
  * fetched; otherwise the grid covers the pool (P is a multiple of 256) and free slots take new voxels. */
-__global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbScene S, const uint32_t* __restrict__ requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t totalItems,
+__global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W,
                                                             uint32_t* __restrict__ counters, DnbStagingTargets T, uint4* __restrict__ ctx, uint32_t P, uint32_t pass, uint32_t drain)
 {
+	/* the request count is read on the device (layout.h DnbWork); a work item = one lane of a request */
+	const uint32_t numRequests = work_requests(W);
+	const uint32_t firstCta = W.firstCta, ctaStride = W.ctaStride;
+	const uint32_t totalItems = work_ctas(W, numRequests) * 128u;
 	__shared__ uint32_t s_warpCount[WAVE_SERVE_THREADS / 32], s_base, s_liveEntries, s_liveSlots, s_entryBase;
 	const uint32_t lane = threadIdx.x & 31u, warpInCta = threadIdx.x >> 5;
 	const uint32_t ltMask = (1u << lane) - 1u;
@@ -416,24 +420,25 @@ struct DnbWaveHost
 };
 static DnbWaveHost g_wave;
 
-__global__ void dn_wave_publish_kernel(const uint32_t* __restrict__ counters, uint32_t pass, uint32_t* __restrict__ hostRing)
+__global__ void dn_wave_publish_kernel(const uint32_t* __restrict__ counters, DnbWork W, uint32_t pass, uint32_t* __restrict__ hostRing)
 {
 	uint32_t* out = hostRing + (pass & 7u) * 4u;
 	out[0] = counters[WC_LIVE0 + (pass & 1u)];
 	out[1] = counters[WC_ENTRIES0 + (pass & 1u)];
 	out[2] = counters[WC_WORK];
+	out[3] = work_ctas(W, work_requests(W)) * 128u; /* the dispatch's work items: the list is exhausted once the work counter has reached this */
 	__threadfence_system();
 }
 
 extern "C" size_t dnb_wave_slot_bytes(void) { return (size_t)WAVE_PLANES * sizeof(uint4); }
 
 /* ctx: WAVE_PLANES * P uint4, P a multiple of 256; counters: WC_WORDS (8) device words */
-extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, uint32_t numRequests, uint32_t firstCta, uint32_t ctaStride, uint32_t numCtas,
+extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32_t* requests, const DnbWork* work,
                                              const DnbStagingTargets* targets, uint4* ctx, uint32_t P, uint32_t* counters, uint32_t* passesOut, cudaStream_t stream)
 {
 	if(passesOut)
 		*passesOut = 0;
-	if(numRequests == 0 || numCtas == 0 || P == 0)
+	if(P == 0)
 		return cudaSuccess;
 	cudaError_t e;
 	if(!g_wave.pinned)
@@ -463,7 +468,6 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 		return e;
 
 	static const int refillMin = [] { const char* v = getenv("DN_B200_WAVE_REFILL"); return v && atoi(v) > 0 ? atoi(v) : 4; }();
-	const uint32_t totalItems = numCtas * 128u;
 
 	static const bool trace = getenv("DN_B200_WAVE_TRACE") != nullptr;
 	uint32_t pass = 0;
@@ -478,10 +482,10 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 				return e;
 			const volatile uint32_t* seen = g_wave.pinned + (look & 7u) * 4u;
 			if(trace)
-				fprintf(stderr, "wave pass %u: %u live slots in %u entries of %u, work counter %u of %u%s\n", look, seen[0], seen[1], P / 32u, seen[2], totalItems, drain ? " (drain mode)" : "");
+				fprintf(stderr, "wave pass %u: %u live slots in %u entries of %u, work counter %u of %u%s\n", look, seen[0], seen[1], P / 32u, seen[2], seen[3], drain ? " (drain mode)" : "");
 			if(seen[0] == 0u)
 				break; /* that pass left no live slot: every voxel of the dispatch is staged */
-			if(seen[2] >= totalItems)
+			if(seen[2] >= seen[3])
 			{
 				/* the list was exhausted by then: no voxel has started since, so the live entries can only have become fewer */
 				drain = true;
@@ -490,10 +494,10 @@ extern "C" cudaError_t dnb_launch_light_wave(const DnbScene* scene, const uint32
 		}
 		const uint32_t serveCtas = drain ? (entryBound + WAVE_SERVE_THREADS / 32 - 1) / (WAVE_SERVE_THREADS / 32) : P / WAVE_SERVE_THREADS;
 		if(serveCtas > 0)
-			{ DNB_LAUNCHED(1); dn_wave_serve_kernel<<<serveCtas, WAVE_SERVE_THREADS, 0, stream>>>(*scene, requests, numRequests, firstCta, ctaStride, totalItems, counters, *targets, ctx, P, pass, drain ? 1u : 0u); }
+			{ DNB_LAUNCHED(1); dn_wave_serve_kernel<<<serveCtas, WAVE_SERVE_THREADS, 0, stream>>>(*scene, requests, *work, counters, *targets, ctx, P, pass, drain ? 1u : 0u); }
 		const uint32_t stepCtas = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)g_wave.stepCtas, (entryBound + 3u) / 4u));
 		{ DNB_LAUNCHED(1); dn_wave_step_kernel<<<stepCtas, 128, 0, stream>>>(*scene, ctx, P, counters, pass, refillMin); }
-		{ DNB_LAUNCHED(1); dn_wave_publish_kernel<<<1, 1, 0, stream>>>(counters, pass, ringDev); }
+		{ DNB_LAUNCHED(1); dn_wave_publish_kernel<<<1, 1, 0, stream>>>(counters, *work, pass, ringDev); }
 		if((e = cudaEventRecord(g_wave.ev[pass & 7u], stream)) != cudaSuccess)
 			return e;
 		if((e = cudaGetLastError()) != cudaSuccess)

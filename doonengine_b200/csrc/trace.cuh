@@ -273,8 +273,20 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 			uint32_t cguard = 0;
 			uint32_t wordIdx = 0xFFFFFFFFu, word = 0;
 			uint32_t bias = 0, offp = 0; /* exact chunk cull (see cull_offsets): c.pos is shifted by the offsets in offp */
-			if(!COUNT && st.lastVoxID == 255u)
-				offp = cull_offsets(DNB_LDG(&slot->bbox), c.step, c.pos, bias);
+			/* the two loads that depend on the slot index leave together: the mask word of the entry cell (needed unless the ray
+			 * enters beyond the culled box) and the bounding-box word, whose top bit also says whether every material of the chunk
+			 * is opaque (layout.h DNB_BBOX_OPAQUE) -- then a set voxel bit IS an opaque hit (SH:351) and the material need not be
+			 * looked at inside the loop */
+			uint32_t bbox = 0;
+			if(!COUNT)
+			{
+				wordIdx = ((uint32_t)c.pos.x + 8u * ((uint32_t)c.pos.y + 8u * (uint32_t)c.pos.z)) >> 5;
+				word = DNB_LDG(slot->mask + wordIdx);
+				bbox = DNB_LDG(&slot->bbox);
+				if(st.lastVoxID == 255u)
+					offp = cull_offsets(bbox, c.step, c.pos, bias);
+			}
+			const bool chunkOpaque = (bbox & DNB_BBOX_OPAQUE) != 0u;
 			while(in_chunk_bounds(c.pos))
 			{
 				if(++cguard > DNB_MAX_CHUNK_STEPS)
@@ -299,7 +311,10 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 					DNB_COUNT(records);
 					st.vox = rec;
 
-					const DnbMaterial material = load_material(S, rec.x >> 24);
+					DnbMaterial material;
+					material.opacity = 1.0f;
+					if(!chunkOpaque)
+						material = load_material(S, rec.x >> 24);
 					const uint32_t thisVoxID = (rec.y & 0xFFFFFF00u) | (rec.x >> 24);
 
 					if(material.opacity == 1.0f)

@@ -223,9 +223,8 @@ class ShardedEngine:
     def light_compute(self, num_diffuse, max_diffuse, time):
         if self.exchange == "peer" and not self.L.DN_b200_peer_capacity_ok(self.e.vol):
             # the request list outgrew the staging arrays (identically on every rank): remap with room to spare
-            need = int(self.e.vol.contents.numLightingRequests)
             self._detach()
-            self._attach(request_cap=2 * need + 4096)
+            self._attach(request_cap=0)  # 0: sized from what is resident now, with room to spare (DN_b200_peer_prepare)
         if not self.L.DN_b200_light_compute(self.e.vol, num_diffuse, max_diffuse, C.c_float(time)):
             raise RuntimeError("DN_b200_light_compute failed: %s" % _last_message())
 

@@ -80,6 +80,17 @@ size_t DN_b200_array_bytes(DNvolume* vol, DNb200array which);
 size_t DN_b200_download(DNvolume* vol, DNb200array which, void* dst, size_t dstBytes);
 void*  DN_b200_array_device_ptr(DNvolume* vol, DNb200array which);
 
+/* ---- the lighting-request count.  Upstream DN_sync_gpu blocks on a glMapBuffer of the whole map and leaves the request list and
+ * vol->numLightingRequests on the host (voxel.c:719-786).  Here the list is built on the device and STAYS there: the lighting kernels
+ * read its length from device memory, so a reading DN_sync_gpu returns without waiting for the GPU and the next DN_update_lighting is
+ * queued right behind it.  vol->numLightingRequests then holds the exact length only if the device happened to be done already;
+ * otherwise it keeps the last exact value it had.  Whoever needs the number asks:
+ *   DN_b200_lighting_request_count()   the exact length (waits for the compaction kernel if necessary) -- also refreshes the field
+ *   DN_b200_fetch_lighting_requests()  the list itself, into vol->lightingRequests (above)
+ *   DN_b200_set_exact_sync(vol, true)  restores upstream's contract: every reading DN_sync_gpu waits, the field is exact at return ---- */
+size_t DN_b200_lighting_request_count(DNvolume* vol);
+void   DN_b200_set_exact_sync(DNvolume* vol, bool exact);
+
 /* ---- instrumentation ---- */
 typedef struct DNb200counters { uint64_t rays, tiles, chunks, voxelSteps, records, voxelsLit, pixels; } DNb200counters;
 /* when enabled the kernels count traversal work (slower); counters accumulate until read with reset */

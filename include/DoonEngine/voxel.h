@@ -12,8 +12,9 @@
  *     there is no demand streaming / LRU eviction (reference voxel.c:1554-1640), so `minChunks` only sizes
  *     the initial pools.  `gpuVoxelLayout` / `numVoxelNodes` are NULL / 0 except right after
  *     DN_b200_mirror_voxel_layout() (DoonEngine/b200.h), which builds a snapshot of this library's own record allocator.
- *   - `lightingRequests` is mirrored to the host lazily (DN_b200_fetch_lighting_requests); the request list
- *     is built on the device.  `numLightingRequests` is valid after every DN_sync_gpu that reads.
+ *   - the request list is built on the device and stays there: `lightingRequests` is mirrored to the host on demand
+ *     (DN_b200_fetch_lighting_requests) and `numLightingRequests` is exact after DN_b200_lighting_request_count() -- or after
+ *     every reading DN_sync_gpu once DN_b200_set_exact_sync(vol, true) has asked for upstream's blocking contract (b200.h).
  *   - raster composition (rasterColorTexture/rasterDepthTexture >= 0) and cubemap skies are not implemented:
  *     DN_draw reports DN_MESSAGE_ERROR and draws without them.
  *

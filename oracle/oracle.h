@@ -15,13 +15,19 @@
  *   binding 3  requests  uint32             voxelLighting.comp:7-10
  *   binding 4  voxels[]  OrbVoxel    16 B   voxelShared.comp:30-36,92-95 ; voxel.c:16-22
  *
- * Parity status: the reference ships no tests, golden vectors or KATs for the
- * GLSL arithmetic and no GLSL implementation can run
- * in the build container or on the GPU box.  The HOST half of the path is
- * pinned by Oracle A (the reference's own voxel.c compiled in place behind a
- * fake-GL shim, oracle/fake_gl.c).  The SHADER half (this restatement) is
- * "parity unpinned by the reference": its fidelity rests on the line-by-line
- * citations in shader_cpu.c and on the determinism rules N1-N10 below.
+ * Parity status: PINNED, both halves, by the reference's own code compiled where it lies (oracle/Makefile; outputs only under
+ * oracle/_ref/, git-ignored; exists only where /root/reference does):
+ *   host half    oracle/_ref/libdoon_ref.so = the reference's voxel.c + glad.c behind the fake-GL shim (oracle/fake_gl.c);
+ *                tests/test_oracle_vs_reference.py: host_cpu.c produces the same buffers, requests, uniforms and matrices, bit for bit.
+ *   shader half  oracle/_ref/libglsl_ref.so = the reference's assets/shaders/voxel{Shared,Lighting,Draw}.comp compiled AS C++
+ *                (oracle/glsl/translate.py does the syntax, glsl_compat.h the types and built-ins, glsl_harness.cpp the dispatch);
+ *                tests/test_glsl_pin.py: shader_cpu.c produces the same pixels, first hits, lit words, visible flags and sample
+ *                counts, bit for bit, over the demo map, a glass / edit / lightingSplit scene and the three synthetic maps.
+ *   fixtures     tests/golden/*.npz are written by the two together (reference host dispatching reference shaders, nothing
+ *                restated: tests/golden/make_golden.py) and checked wherever the suite runs, incl. the GPU box.
+ * The reference ships no tests, golden vectors or KATs of its own.  What remains DEFINED rather than pinned
+ * are the points where GLSL itself leaves the result to the implementation or the shaders race -- rules N1-N11 below; both
+ * implementations (and the CUDA kernels) follow the same rules, so they can be compared bit for bit.
  *
  * Determinism rules added where the reference is racy / implementation
  * defined:

@@ -133,6 +133,19 @@ def get_params(src):
     return out
 
 
+def fill_local_indices(hits, map_view, chunk_view):
+    """the reference's shaders, run as they are (GlslEngine / RefEngine(glsl=True)), report a first hit as (tile, record index); the
+    voxel's index inside its chunk follows from the chunk's bit mask: the record's rank among the chunk's records = the rank of the
+    voxel's bit among the set bits (get_voxel_index, voxelShared.comp:150-169)."""
+    flat = hits.reshape(-1)
+    for k in np.nonzero((flat["status"] == 2) & (flat["localIndex"] == 0xFFFFFFFF))[0]:
+        tile = int(flat["mapIndex"][k])
+        rank = int(flat["recordIndex"][k]) - int(map_view["voxelIndex"][tile])
+        bits = np.unpackbits(chunk_view["bitMask"][tile].astype("<u4").view(np.uint8), bitorder="little")
+        flat["localIndex"][k] = int(np.nonzero(bits)[0][rank])
+    return hits
+
+
 class _EngineBase:
     """shared helpers: state export in a layout-independent form."""
 
@@ -349,6 +362,8 @@ class GlslEngine(OracleEngine):
         hits = np.zeros((h, w), HIT_DT) if want_hits else None
         buf = self._buffers()
         self.G.glsl_draw(C.byref(buf), C.byref(u), w, h, img.ctypes.data, hits.ctypes.data if want_hits else None)
+        if want_hits:
+            fill_local_indices(hits, self.map_view(), self.chunk_view())
         return (img, hits) if want_hits else img
 
     def update_lighting(self, num_diffuse=1, max_diffuse=1000, time=1.0):
@@ -499,6 +514,8 @@ class RefEngine(_EngineBase):
         img = px.reshape(h, w, 4).copy()
         if want_hits:
             hits = _view(self.L.fgl_texture_hits(tex), HIT_DT, w * h).reshape(h, w).copy()
+            if getattr(self, "G", None) is not None:
+                fill_local_indices(hits, self.map_view(), self.chunk_view())
             return img, hits
         return img
 

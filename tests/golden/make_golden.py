@@ -2,8 +2,11 @@
 
     python tests/golden/make_golden.py
 
-Everything is produced by the REFERENCE's own host code (voxel.c compiled in place, oracle/_ref) driving the CPU
-restatement of its shaders (oracle/shader_cpu.c) -- see oracle/oracle.h for the parity status of each half.
+Everything is produced by the REFERENCE's own code, both halves, nothing restated: its host (voxel.c compiled in place behind the
+fake-GL shim, oracle/_ref/libdoon_ref.so) dispatching its own compute shaders (assets/shaders/*.comp compiled as C++ where they lie,
+oracle/glsl/ -> oracle/_ref/libglsl_ref.so).  The implementation-defined GLSL built-ins and the three data races are fixed as
+oracle/oracle.h N1-N6 says.  tests/test_oracle_golden.py checks the hand restatement (oracle/shader_cpu.c + host_cpu.c) against these
+files wherever the suite runs; tests/test_glsl_pin.py compares the two shader implementations directly where /root/reference exists.
 
   demo.voxvol        the reference's bundled map, re-serialised by the reference's own DN_load_volume + DN_save_volume
                      (byte-identical to assets/volumes/demo.voxvol; checked below)
@@ -136,7 +139,7 @@ def main():
     O.build()
     make_picks()
     # --- demo.voxvol through the reference's own load + save ---
-    ref = O.RefEngine(voxvol=REF_DEMO, min_chunks=256)
+    ref = O.RefEngine(voxvol=REF_DEMO, min_chunks=256, glsl=True)
     ref.L.DN_save_volume.restype = C.c_bool
     ref.L.DN_save_volume.argtypes = [C.c_char_p, C.c_void_p]
     dst = os.path.join(HERE, "demo.voxvol")
@@ -150,7 +153,7 @@ def main():
     ref.close()
 
     # --- mixed-material scene through the reference host ---
-    ref = O.RefEngine(map_size=(6, 4, 6), min_chunks=256)
+    ref = O.RefEngine(map_size=(6, 4, 6), min_chunks=256, glsl=True)
     scenes.build(ref, scenes.mixed_materials(), **scenes.mixed_camera())
     out = {}
     run_protocol(ref, out)

@@ -27,7 +27,8 @@ def _run(engine, g, prefix=""):
     for k in range(FRAMES):
         img, hits = engine.draw(W, H, want_hits=True)
         if k == 0:
-            assert np.array_equal(hits["status"], g[prefix + "hit_status"])
+            # the golden comes from the reference's own shaders, which tell "hit" (2) from "no hit" (1) but not whether a ray missed the map box
+            assert np.array_equal(hits["status"] == 2, g[prefix + "hit_status"] == 2)
             hit = hits["status"] == 2
             assert np.array_equal(hits["mapIndex"][hit], g[prefix + "hit_tile"][hit])
             assert np.array_equal(hits["localIndex"][hit], g[prefix + "hit_voxel"][hit])

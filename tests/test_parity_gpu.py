@@ -71,7 +71,8 @@ def test_demo_map_against_golden(dn):
     for k in range(FRAMES):
         img, hits = e.draw(W, H, want_hits=True)
         if k == 0:
-            assert np.array_equal(hits["status"], g["hit_status"])
+            # the golden comes from the reference's own shaders, which tell "hit" (2) from "no hit" (1) but not whether a ray missed the map box
+            assert np.array_equal(hits["status"] == 2, g["hit_status"] == 2)
             hit = hits["status"] == 2
             assert np.array_equal(hits["mapIndex"][hit], g["hit_tile"][hit])
             assert np.array_equal(hits["localIndex"][hit], g["hit_voxel"][hit])

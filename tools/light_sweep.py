@@ -60,6 +60,6 @@ for name, knobs in variants:
         if f >= 2:
             times.append(a.elapsed_time(b))
             dtimes.append(d0.elapsed_time(d1))
-    rec = {"config": cfg, "kernel": name, "knobs": knobs, "env": {k: v for k, v in os.environ.items() if k.startswith("DN_B200_")}, "wave_passes": int(e.stats()["lastWavePasses"]), "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "draw_ms_median": float(np.median(dtimes)), "requests": int(e.vol.contents.numLightingRequests)}
+    rec = {"config": cfg, "kernel": name, "knobs": knobs, "env": {k: v for k, v in os.environ.items() if k.startswith("DN_B200_")}, "wave_passes": int(e.stats()["lastWavePasses"]), "light_ms_median": float(np.median(times)), "light_ms_min": float(min(times)), "draw_ms_median": float(np.median(dtimes)), "requests": e.num_requests()}
     print(json.dumps(rec), flush=True)
     out.append(rec)
