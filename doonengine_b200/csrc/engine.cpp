@@ -135,7 +135,7 @@ void device_destroy(VolumeImpl* v)
 	}
 	device_free(v->tileSlot); device_free(v->occ64); device_free(v->visible); device_free(v->propagate); device_free(v->forced);
 	device_free(v->slots); device_free(v->records); device_free(v->materials); device_free(v->requests); device_free(v->staging);
-	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->waveCtx); device_free(v->pickRays); device_free(v->pickHits); device_free(v->blob); device_free(v->litCounter);
+	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->waveCtx); device_free(v->pickRays); device_free(v->pickHits); device_free(v->blobs[0]); device_free(v->blobs[1]); device_free(v->litCounter);
 	device_free(v->mailbox); device_free(v->barrierStatus);
 	v->peerAttached = false;
 	for(int slot = 0; slot < 2; slot++)
@@ -145,11 +145,16 @@ void device_destroy(VolumeImpl* v)
 		v->tuner.begin[slot] = v->tuner.end[slot] = nullptr;
 		v->tuner.slotKernel[slot] = -1;
 	}
-	if(v->pinnedBlob) cudaFreeHost(v->pinnedBlob);
+	for(int k = 0; k < 2; k++)
+	{
+		if(v->pinnedBlobs[k]) cudaFreeHost(v->pinnedBlobs[k]);
+		if(v->blobDone[k]) cudaEventDestroy(v->blobDone[k]);
+		v->pinnedBlobs[k] = nullptr;
+		v->pinnedBlobCaps[k] = 0;
+		v->blobDone[k] = nullptr;
+	}
 	if(v->pinnedScalars) cudaFreeHost(v->pinnedScalars);
 	if(v->counters) cudaFree(v->counters);
-	v->pinnedBlob = nullptr;
-	v->pinnedBlobCap = 0;
 	v->pinnedScalars = nullptr;
 	v->counters = nullptr;
 }
@@ -589,26 +594,29 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 	const size_t offRecords = offHeaders + count * sizeof(DnbSlot);
 	const size_t blobBytes = offRecords + count * 512 * sizeof(uint4);
 
-	if(blobBytes > v->pinnedBlobCap)
-	{
-		/* the previous batch may still be in flight from this buffer */
-		cudaStreamSynchronize(c.uploadStream);
-		if(v->pinnedBlob)
-			cudaFreeHost(v->pinnedBlob);
-		v->pinnedBlob = nullptr;
-		v->pinnedBlobCap = 0;
-		if(!cuda_ok(cudaMallocHost((void**)&v->pinnedBlob, blobBytes), "pinned upload blob"))
-			return false;
-		v->pinnedBlobCap = blobBytes;
-	}
-	else
-		cudaStreamSynchronize(c.uploadStream); /* single staging buffer: wait for the previous batch's copy */
-	if(!device_reserve(v->blob, blobBytes, false, false, "device upload blob"))
+	/* this batch's buffer pair; wait only for the batch that used it last (two batches ago) */
+	const unsigned turn = v->blobTurn++ & 1u;
+	if(!v->blobDone[turn] && !cuda_ok(cudaEventCreateWithFlags(&v->blobDone[turn], cudaEventDisableTiming), "event create"))
 		return false;
+	cuda_ok(cudaEventSynchronize(v->blobDone[turn]), "upload batch"); /* (an event never recorded counts as complete) */
+	if(blobBytes > v->pinnedBlobCaps[turn])
+	{
+		if(v->pinnedBlobs[turn])
+			cudaFreeHost(v->pinnedBlobs[turn]);
+		v->pinnedBlobs[turn] = nullptr;
+		v->pinnedBlobCaps[turn] = 0;
+		const size_t want = blobBytes + blobBytes / 4; /* batches of an edit stream vary in size: leave room instead of reallocating pinned memory every other frame */
+		if(!cuda_ok(cudaMallocHost((void**)&v->pinnedBlobs[turn], want), "pinned upload blob"))
+			return false;
+		v->pinnedBlobCaps[turn] = want;
+	}
+	if(!device_reserve(v->blobs[turn], v->pinnedBlobCaps[turn], false, false, "device upload blob"))
+		return false;
+	unsigned char* const pinnedBlob = v->pinnedBlobs[turn];
 
-	DnbUploadItem* hItems = reinterpret_cast<DnbUploadItem*>(v->pinnedBlob + offItems);
-	DnbSlot* hHeaders = reinterpret_cast<DnbSlot*>(v->pinnedBlob + offHeaders);
-	uint4* hRecords = reinterpret_cast<uint4*>(v->pinnedBlob + offRecords);
+	DnbUploadItem* hItems = reinterpret_cast<DnbUploadItem*>(pinnedBlob + offItems);
+	DnbSlot* hHeaders = reinterpret_cast<DnbSlot*>(pinnedBlob + offHeaders);
+	uint4* hRecords = reinterpret_cast<uint4*>(pinnedBlob + offRecords);
 
 	/* parallel pack: worker t owns a contiguous range of items and packs their records back to back into its arena */
 	uint8_t opaque[256];
@@ -710,19 +718,21 @@ static bool upload_batch(VolumeImpl* v, const PendingItem* items, size_t count)
 	cuda_ok(cudaEventRecord(c.evComputeDone, cs), "event record");
 	cuda_ok(cudaStreamWaitEvent(c.uploadStream, c.evComputeDone, 0), "stream wait");
 
-	unsigned char* dBlob = v->blob.ptr;
-	bool ok = cuda_ok(cudaMemcpyAsync(dBlob + offItems, v->pinnedBlob + offItems, offRecords, cudaMemcpyHostToDevice, c.uploadStream), "upload headers");
+	unsigned char* dBlob = v->blobs[turn].ptr;
+	bool ok = cuda_ok(cudaMemcpyAsync(dBlob + offItems, pinnedBlob + offItems, offRecords, cudaMemcpyHostToDevice, c.uploadStream), "upload headers");
 	for(unsigned t = 0; t < workers && ok; t++)
 	{
 		if(arenaUsed[t] == 0)
 			continue;
 		const size_t at = offRecords + (count * t / workers) * 512 * sizeof(uint4);
-		ok = cuda_ok(cudaMemcpyAsync(dBlob + at, v->pinnedBlob + at, arenaUsed[t] * sizeof(uint4), cudaMemcpyHostToDevice, c.uploadStream), "upload records");
+		ok = cuda_ok(cudaMemcpyAsync(dBlob + at, pinnedBlob + at, arenaUsed[t] * sizeof(uint4), cudaMemcpyHostToDevice, c.uploadStream), "upload records");
 	}
 	const uint32_t mapSize[3] = {vol->mapSize.x, vol->mapSize.y, vol->mapSize.z};
 	ok = ok && cuda_ok(dnb_launch_scatter(reinterpret_cast<const DnbUploadItem*>(dBlob + offItems), reinterpret_cast<const DnbSlot*>(dBlob + offHeaders),
 	                                      reinterpret_cast<const uint4*>(dBlob + offRecords), (uint32_t)count, mapSize, v->blocks, v->tileSlot.ptr, v->occ64.ptr, v->visible.ptr,
 	                                      v->slots.ptr, v->records.ptr, c.uploadStream), "scatter kernel");
+
+	cuda_ok(cudaEventRecord(v->blobDone[turn], c.uploadStream), "event record");
 
 	v->stats.bytesUploaded += count * (sizeof(DnbUploadItem) + sizeof(DnbSlot)) + recordBytes;
 	v->stats.lastEnqueueHostMs += (float)(host_now_ms() - tPack1);
@@ -1375,26 +1385,30 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 	}
 	cudaGetLastError(); /* cudaErrorNotReady from the queries above is not an error */
 
+	/* candidates of the automatic choice: the warp-per-request and the persistent kernel.  The wavefront pair (mode 3) is not among
+	 * them: measured on B200 after round 2's dropped-item fix it is slower than the persistent kernel on every configuration
+	 * (profiles/r2_light.md), so timing it on live dispatches would only cost frames; it stays selectable explicitly. */
+	const int NUM_AUTO = 2;
 	int k;
 	const uint64_t n = t.dispatches++;
-	if(t.samples[0] < 2 || t.samples[1] < 2 || t.samples[2] < 2)
+	if(t.samples[0] < 2 || t.samples[1] < 2)
 	{
 		/* round robin over the kernels that still lack two timings (the first dispatch of a volume is never timed) */
-		k = (int)(n % 3u);
-		for(int tries = 0; tries < 3 && t.samples[k] >= 2; tries++)
-			k = (k + 1) % 3;
+		k = (int)(n % (unsigned)NUM_AUTO);
+		for(int tries = 0; tries < NUM_AUTO && t.samples[k] >= 2; tries++)
+			k = (k + 1) % NUM_AUTO;
 	}
 	else
 	{
 		/* hysteresis: the kernel that ran last keeps running unless another one is at least 5 % faster */
-		const int last = t.lastKernel;
+		const int last = t.lastKernel < NUM_AUTO ? t.lastKernel : 0;
 		int best = 0;
-		for(int o = 1; o < 3; o++)
+		for(int o = 1; o < NUM_AUTO; o++)
 			if(t.nsPerCta[o] < t.nsPerCta[best])
 				best = o;
 		k = (best != last && t.nsPerCta[best] < 0.95 * t.nsPerCta[last]) ? best : last;
 		if((n & 63u) == 63u)
-			k = (k + 1 + (int)((n >> 6) & 1u)) % 3;  /* keep the other kernels' estimates fresh, in turn */
+			k = (k + 1) % NUM_AUTO;  /* keep the other kernel's estimate fresh */
 		else
 			t.lastKernel = k;
 	}

@@ -89,9 +89,13 @@ struct VolumeImpl
 	DeviceArray<int4>               pickHits;
 	DeviceArray<uint4>              waveCtx;   /* context pool of the wavefront lighting kernels (light_wave.cuh), allocated on first use */
 	DeviceArray<unsigned long long> litCounter; /* voxel lighting updates committed since creation */
-	DeviceArray<unsigned char>      blob;      /* device side of the upload batch */
-	unsigned char* pinnedBlob = nullptr;
-	size_t         pinnedBlobCap = 0;
+	/* upload batches travel through two (pinned host, device) buffer pairs in rotation: the host packs batch k+1 while the copy and
+	 * scatter of batch k are still queued behind the GPU's frame (with one pair the host had to wait for the GPU at every batch) */
+	DeviceArray<unsigned char>      blobs[2];
+	unsigned char* pinnedBlobs[2] = {nullptr, nullptr};
+	size_t         pinnedBlobCaps[2] = {0, 0};
+	cudaEvent_t    blobDone[2] = {nullptr, nullptr}; /* the batch that last used the pair has been scattered */
+	unsigned       blobTurn = 0;
 	uint32_t*      pinnedScalars = nullptr;    /* read-back of the request count */
 	DnbCounters*   counters = nullptr;         /* device, NULL when instrumentation is off */
 	bool           forcedDirty = false;

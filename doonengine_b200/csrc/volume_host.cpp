@@ -12,6 +12,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 extern "C" void (*g_DN_message_callback)(DNmessageType, DNmessageSeverity, const char*) = nullptr;
 
@@ -36,6 +39,20 @@ void touch_tile(VolumeImpl* v, size_t mapIndex)
 		return;
 	v->touchedFlag[mapIndex] = 1;
 	v->touched.push_back((uint32_t)mapIndex);
+}
+
+/* The chunk array of a large map is hundreds of megabytes to gigabytes, and edits land all over it: with 4 KB pages every access
+ * also misses the TLB.  Ask for huge pages where the kernel leaves that to madvise (a hint; failure is harmless). */
+static void advise_huge(void* p, size_t bytes)
+{
+#if defined(__linux__)
+	const uintptr_t a = ((uintptr_t)p + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
+	const uintptr_t e = ((uintptr_t)p + bytes) & ~(((uintptr_t)2 << 20) - 1);
+	if(e > a)
+		madvise((void*)a, (size_t)(e - a), MADV_HUGEPAGE);
+#else
+	(void)p; (void)bytes;
+#endif
 }
 
 /* voxel.c:1353-1363; numVoxelsGpu deliberately survives, as upstream */
@@ -80,6 +97,10 @@ extern "C" DNvolume* DN_create_volume(DNuvec3 mapSize, unsigned int minChunks)
 	vol->mapSize = mapSize;
 	vol->map = (DNchunkHandle*)DN_MALLOC(sizeof(DNchunkHandle) * (tiles ? tiles : 1));
 	vol->chunks = (DNchunk*)DN_MALLOC(sizeof(DNchunk) * numChunks);
+	if(vol->chunks)
+		advise_huge(vol->chunks, sizeof(DNchunk) * numChunks);
+	if(vol->map)
+		advise_huge(vol->map, sizeof(DNchunkHandle) * (tiles ? tiles : 1));
 	vol->materials = (DNmaterial*)DN_MALLOC(sizeof(DNmaterial) * DN_MAX_MATERIALS);
 	vol->lightingRequests = (GLuint*)DN_MALLOC(sizeof(GLuint) * numChunks);
 	vol->gpuVoxelLayout = NULL; /* mirrored on demand, see DN_b200 docs */
@@ -516,6 +537,8 @@ extern "C" bool DN_set_max_chunks(DNvolume* vol, size_t num)
 	if(num == 0)
 		num = 1;
 	DNchunk* grown = (DNchunk*)DN_REALLOC(vol->chunks, sizeof(DNchunk) * num);
+	if(grown)
+		advise_huge(grown, sizeof(DNchunk) * num);
 	if(!grown)
 	{
 		report(DN_MESSAGE_CPU_MEMORY, DN_MESSAGE_ERROR, "failed to reallocate memory for chunks");
@@ -836,9 +859,41 @@ extern "C" void DN_set_view_projection_matrices(DNvolume* vol, float aspectRatio
  * material is DN_MATERIAL_EMPTY is removed (DN_remove_voxel).  Positions outside the map are skipped.  Returns the edits applied. */
 extern "C" size_t DN_b200_set_voxels(DNvolume* vol, size_t count, const DNivec3* positions, const DNcompressedVoxel* voxels)
 {
+	/* The edits of a stream land all over a map of hundreds of megabytes: every one of them misses the cache three times in a row
+	 * (tile handle -> chunk header -> voxel).  The list is known in advance, so the handle of edit i + 16 and the chunk lines of edit
+	 * i + 8 are prefetched while edit i is applied (prefetches are hints: a chunk array that moves in between costs nothing). */
+	const size_t AHEAD = 16;
+	auto tile_of = [&](size_t i, DNivec3* chunkPos) -> long long
+	{
+		const DNivec3 p = positions[i];
+		if(p.x < 0 || p.y < 0 || p.z < 0)
+			return -1;
+		DNivec3 mapPos;
+		DN_separate_position(p, &mapPos, chunkPos);
+		if(!DN_in_map_bounds(vol, mapPos))
+			return -1;
+		return (long long)DN_FLATTEN_INDEX(mapPos, vol->mapSize);
+	};
 	size_t applied = 0;
 	for(size_t i = 0; i < count; i++)
 	{
+		DNivec3 cp;
+		if(i + AHEAD < count)
+		{
+			const long long t = tile_of(i + AHEAD, &cp);
+			if(t >= 0)
+				__builtin_prefetch(&vol->map[t], 0, 1);
+		}
+		if(i + AHEAD / 2 < count)
+		{
+			const long long t = tile_of(i + AHEAD / 2, &cp);
+			if(t >= 0 && vol->map[t].flag != 0 && vol->map[t].chunkIndex < vol->chunkCap)
+			{
+				const DNchunk* ch = &vol->chunks[vol->map[t].chunkIndex];
+				__builtin_prefetch(ch, 1, 1);
+				__builtin_prefetch(&ch->voxels[cp.x][cp.y][cp.z], 1, 1);
+			}
+		}
 		DNivec3 mapPos, chunkPos;
 		if(positions[i].x < 0 || positions[i].y < 0 || positions[i].z < 0)
 			continue;
