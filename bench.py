@@ -154,10 +154,11 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(kernel, config):
-    """measured DRAM bytes per launch of `kernel` on bench config `config` from the committed ncu captures (profiles/kernel_traffic.json),
-    or None when that combination has not been captured."""
-    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+def profile_of(kernel, config):
+    """what ncu measured for `kernel` on bench config `config` with THIS round's build (profiles/r2_kernels.json, written by
+    tools/ncu_table.py from the captures of tools/r2_profile.sh): DRAM bytes per launch, achieved L2 / DRAM GB/s, issue-slot utilisation,
+    active lanes per instruction.  None when that combination has not been captured -- nothing is borrowed from another config."""
+    path = os.path.join(ROOT, "profiles", "r2_kernels.json")
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f).get("%s@%s" % (kernel, config))
@@ -307,7 +308,7 @@ def run_ours(args):
 
     L = dn.lib()
     dn.init(device=local)
-    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "auto": 2, "wave": 3}[args.light_kernel])
+    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "auto": 2, "wave": 3, "spread": 4}[args.light_kernel])
     # a non-default stream shared by torch (events, collectives, copies) and the library's kernels
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)
@@ -465,8 +466,13 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         wall0 = time.perf_counter()
         region0 = ev()
         region0.record(stream)
+        flush_marks = []
         for i in range(steps):
+            f0, f1 = ev(), ev()
+            f0.record(stream)
             flush.fill_(i & 0xFF)
+            f1.record(stream)
+            flush_marks.append((f0, f1))
             m, r = step(k0 + i, not read_back, read_back)  # the end-to-end region is timed as ONE piece: no per-phase events inside it
             if m is not None:
                 all_marks.append(m)
@@ -488,7 +494,8 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         lit = e.stats()["voxelsLit"] - lit0
         # [5] whole step, [6] lighting phases: summed per rank BEFORE the max over ranks (a per-phase max would count a wait twice)
         # [7] the whole region in one piece, L2 flushes and host gaps included: what the end-to-end number is quoted on
-        phases = np.concatenate([phases, [phases.sum(), phases[2] + phases[3], region0.elapsed_time(drain1)]])
+        flush_ms = sum(a.elapsed_time(b) for a, b in flush_marks)
+        phases = np.concatenate([phases, [phases.sum(), phases[2] + phases[3], region0.elapsed_time(drain1), flush_ms]])
         return phases, lit, reqs, clocks, wall
 
     # ---- untimed pre-roll: lets the library's lighting-kernel selection settle (auto mode times both kernels on its first
@@ -524,8 +531,9 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
     phases = reduce_max(phases)
     phases2 = reduce_max(phases2)
     K = max(steps, 1)
-    draw_ms, sync_ms, light_ms, commit_ms, rb_ms, frame_ms, light_total_ms, _ = (phases / K).tolist()
+    draw_ms, sync_ms, light_ms, commit_ms, rb_ms, frame_ms, light_total_ms, _, _ = (phases / K).tolist()
     frame2_ms = float(phases2[7] / K)
+    flush2_ms = float(phases2[8] / K)
     light_total_s = phases[6] / 1000.0
     value = lit / light_total_s if light_total_s > 0 else 0.0
     e2e_value = lit2 / (phases2[7] / 1000.0) if phases2[7] > 0 else 0.0
@@ -558,16 +566,20 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         achieved = b_light / (light_ms / 1000.0) / 1e9 if light_ms > 0 else 0.0
         b_draw = algorithmic_bytes_draw(cd)
         st_ = e.stats()
-        light_name = max((("dn_light_kernel", st_["lightLaunchesWarp"]), ("dn_light_flat_kernel", st_["lightLaunchesFlat"]), ("dn_wave_step_kernel", st_["lightLaunchesWave"])), key=lambda kv: kv[1])[0]
-        traffic = traffic_from_profile(light_name, config)
+        light_name = max((("dn_light_kernel", st_["lightLaunchesWarp"]), ("dn_light_flat_kernel", st_["lightLaunchesFlat"]), ("dn_wave_step_kernel", st_["lightLaunchesWave"]),
+                          ("dn_light_spread_kernel", st_["lightLaunchesSpread"])), key=lambda kv: kv[1])[0]
+        prof = profile_of(light_name, config)
         roofline = {"kernel": light_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": traffic,
+                    "traffic": prof["dram_bytes"] if prof else None,
+                    "ncu": ({k_: prof[k_] for k_ in ("time_us", "dram_gbs", "l2_gbs", "issue_active_pct", "lanes_per_instruction", "l1_hit_pct", "l2_hit_pct", "registers", "report")}
+                            if prof else None),
                     "algorithmic_bytes_per_launch": b_light, "compulsory_bytes_per_launch": b_compulsory,
                     "compulsory_frac": (b_compulsory / (light_ms / 1000.0) / 1e9 / peak) if light_ms > 0 else 0.0,
                     "per_voxel": {k: cl[k] / max(cl["voxelsLit"], 1) for k in ("rays", "tiles", "chunks", "voxelSteps", "records")},
                     "draw": {"kernel": "dn_draw_kernel", "algorithmic_bytes_per_launch": b_draw, "achieved": b_draw / (draw_ms / 1000.0) / 1e9 if draw_ms > 0 and world == 1 else None,
                              "unit": "GB/s", "rays": cd["rays"], "tiles_per_ray": cd["tiles"] / max(cd["rays"], 1), "voxel_steps_per_ray": cd["voxelSteps"] / max(cd["rays"], 1)},
-                    "note": "latency/divergence-bound gather traversal; the HBM fraction is expected to be small (SURVEY.md 8d)"}
+                    "note": "issue-bound gather traversal under divergence: `achieved` counts ALGORITHMIC bytes (SURVEY.md 8d), almost all of which are L1 / L2 hits -- "
+                            "`traffic` is what actually reached DRAM and `ncu` the achieved L2 GB/s, issue-slot utilisation and active lanes per instruction of one captured launch"}
 
     cpu = None
     if rank == 0 and world == 1 and want_cpu and config in ("c3", "c5"):
@@ -597,13 +609,14 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "resolution": [w, h], "parallelism": ("map replicated, request CTAs and 16-pixel rows interleaved x%d, exchange=%s" % (world, sh.exchange)) if world > 1 else "1 GPU",
-                       "light_kernel": {"mode": args.light_kernel, "dispatches_warp_per_request": int(stats["lightLaunchesWarp"]), "dispatches_persistent": int(stats["lightLaunchesFlat"]), "dispatches_wavefront": int(stats["lightLaunchesWave"]),
+                       "light_kernel": {"mode": args.light_kernel, "dispatches_warp_per_request": int(stats["lightLaunchesWarp"]), "dispatches_persistent": int(stats["lightLaunchesFlat"]), "dispatches_wavefront": int(stats["lightLaunchesWave"]), "dispatches_spread": int(stats["lightLaunchesSpread"]),
                                         "wavefront_passes_last": int(stats["lastWavePasses"]),
-                                        "ns_per_4_requests": {"warp": stats["nsPerCtaWarp"], "persistent": stats["nsPerCtaFlat"], "wavefront": stats["nsPerCtaWave"]}}, "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
+                                        "ns_per_4_requests": {"warp": stats["nsPerCtaWarp"], "persistent": stats["nsPerCtaFlat"], "wavefront": stats["nsPerCtaWave"], "spread": stats["nsPerCtaSpread"]}}, "l2": "flushed between steps (256 MiB device write, outside the timed events)", "resident_chunks": int(stats["residentChunks"]),
                        "resident_records": int(stats["residentRecords"]), "requests_per_step": reqs / K, "voxels_lit_per_step": lit / K, "build_s": t_build},
             "frame_ms": {"draw": draw_ms, "sync_compact": sync_ms, "light_kernel": light_ms, "commit": commit_ms, "frame": frame_ms, "frame_with_readback": frame2_ms,
                          "wall_per_step_incl_flush": 1000.0 * wall / K},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8192 + 2416, "d2h_bytes_per_step": fb_bytes + 4, "ms_per_step": frame2_ms,
+                    "l2_flush_ms_per_step": flush2_ms, "ms_per_step_without_l2_flush": frame2_ms - flush2_ms,
                     "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps frame k+1; N > 1: every replica copies the rows it drew into one shared pinned mapping); timed as ONE region from the first draw to the last copy landing, L2 flushes and host gaps between steps included"},
             "gpu_launches": launches,
             "host_ms_per_step_e2e": {k_: (1000.0 * v_ / max(host_s["steps"], 1)) for k_, v_ in host_s.items() if k_ != "steps"},
@@ -644,7 +657,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the second timed block (full-size sparse 2048^3 map at 3840x2160, reported as \"c3_4k\")")
     ap.add_argument("--c3-steps", type=int, default=8, help="timed frames of the c3_4k block (config 3 names 8 frames)")
-    ap.add_argument("--light-kernel", default="auto", choices=["auto", "flat", "warp", "wave"], help="auto (default): the library times its three lighting kernels on live dispatches and runs the fastest one")
+    ap.add_argument("--light-kernel", default="auto", choices=["auto", "flat", "warp", "wave", "spread"], help="auto (default): the library times its candidate lighting kernels on live dispatches and runs the fastest one")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"], help="N > 1: kernels exchange over peer memory (default) or host-driven NCCL all-gathers")
     ap.add_argument("--sampler-ms", type=float, default=10.0, help="NVML clock sampling period during the timed region (0 = off)")
     args = ap.parse_args()

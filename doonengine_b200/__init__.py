@@ -83,7 +83,8 @@ class DNb200stats(C.Structure):
                 ("lightLaunchesWarp", C.c_uint64), ("lightLaunchesFlat", C.c_uint64), ("nsPerCtaWarp", C.c_float), ("nsPerCtaFlat", C.c_float),
                 ("lastScanHostMs", C.c_float), ("lastPackHostMs", C.c_float), ("lastEnqueueHostMs", C.c_float),
                 ("lightLaunchesWave", C.c_uint64), ("nsPerCtaWave", C.c_float), ("lastWavePasses", C.c_uint32), ("pad0", C.c_uint32),
-                ("nodeSplits", C.c_uint64), ("nodeMerges", C.c_uint64), ("usedNodes", C.c_uint64), ("freeNodes", C.c_uint64), ("recordTop", C.c_uint64)]
+                ("nodeSplits", C.c_uint64), ("nodeMerges", C.c_uint64), ("usedNodes", C.c_uint64), ("freeNodes", C.c_uint64), ("recordTop", C.c_uint64),
+                ("lightLaunchesSpread", C.c_uint64), ("nsPerCtaSpread", C.c_float), ("pad1", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -1343,28 +1343,37 @@ static int light_kernel_choice()
 	if(g_lightKernel < 0)
 	{
 		const char* env = getenv("DN_B200_LIGHT_KERNEL");
-		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : (env && strcmp(env, "flat") == 0) ? 1 : (env && strcmp(env, "wave") == 0) ? 3 : 2;
+		g_lightKernel = (env && strcmp(env, "warp") == 0) ? 0 : (env && strcmp(env, "flat") == 0) ? 1 : (env && strcmp(env, "wave") == 0) ? 3 : (env && strcmp(env, "spread") == 0) ? 4 : 2;
 	}
 	return g_lightKernel;
 }
 
-extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = (which >= 0 && which <= 3) ? which : 2; }
+extern "C" void DN_b200_set_light_kernel(int which) { g_lightKernel = (which >= 0 && which <= 4) ? which : 2; }
 extern "C" int DN_b200_get_light_kernel(void) { return light_kernel_choice(); }
 
-/* Auto mode.  The three kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a
- * question of speed, and that depends on the scene: short rays that end together favour one warp per request, rays of very
- * different length the persistent state machine (2.6x on the sparse map), and large dispatches of such rays the wavefront pair.
- * Every dispatch is bracketed by two events (no synchronisation: they are read one or two dispatches later, once they have completed
- * anyway); the first dispatches rotate through the kernels until each has two timings (the very first one, the jitter-free first
- * sample, is not representative and is not used), then the fastest one runs, with 5 % hysteresis, and the others are re-timed in
- * turn every 64th dispatch in case the camera or the map has changed. */
-static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, int* slotOut)
+extern "C" bool dnb_light_spread_usable(uint32_t numDiffuseSamples, uint32_t specularBounceLimit);
+extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint32_t* requests, const DnbWork* work, uint32_t gridCtas, const DnbStagingTargets* targets, cudaStream_t stream);
+
+/* kernel indices used below: 0 warp per request (light.cu), 1 persistent state machine (light_flat.cuh), 2 wavefront pair
+ * (light_wave.cuh), 3 one warp per voxel with its rays spread over the lanes (light_spread.cuh).
+ *
+ * Auto mode.  The kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a question
+ * of speed, and that depends on the scene: short rays that end together favour one warp per request, rays of very different length
+ * the persistent state machine, and dispatches too small to fill the machine with one thread per voxel the spread kernel (a
+ * candidate only up to SPREAD_MAX_REQUESTS requests: it spends a warp per voxel).  Every dispatch is bracketed by two events (no
+ * synchronisation: they are read one or two dispatches later, once they have completed anyway); the first dispatches rotate through
+ * the candidates until each has two timings (the very first one, the jitter-free first sample, is not representative and is not
+ * used), then the fastest one runs, with 5 % hysteresis, and the others are re-timed in turn every 64th dispatch in case the camera
+ * or the map has changed.  The wavefront pair is not a candidate: measured on B200 after round 2's dropped-item fix it is slower
+ * than the persistent kernel on every configuration (profiles/r2_light.md); it stays selectable explicitly. */
+static const size_t SPREAD_MAX_REQUESTS = 8192;
+static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool spreadEligible, cudaStream_t s, int* slotOut)
 {
 	VolumeImpl::LightTuner& t = v->tuner;
 	*slotOut = -1;
 	const int mode = light_kernel_choice();
 	if(mode != 2)
-		return mode == 3 ? 2 : mode;
+		return mode == 3 ? 2 : mode == 4 ? (spreadEligible ? 3 : 0) : mode;
 
 	/* harvest finished timings */
 	for(int slot = 0; slot < 2; slot++)
@@ -1385,30 +1394,38 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, cudaStream_t s, in
 	}
 	cudaGetLastError(); /* cudaErrorNotReady from the queries above is not an error */
 
-	/* candidates of the automatic choice: the warp-per-request and the persistent kernel.  The wavefront pair (mode 3) is not among
-	 * them: measured on B200 after round 2's dropped-item fix it is slower than the persistent kernel on every configuration
-	 * (profiles/r2_light.md), so timing it on live dispatches would only cost frames; it stays selectable explicitly. */
-	const int NUM_AUTO = 2;
-	int k;
+	int cand[3] = {0, 1, 3};
+	const int numCand = spreadEligible ? 3 : 2;
+	int k = -1;
 	const uint64_t n = t.dispatches++;
-	if(t.samples[0] < 2 || t.samples[1] < 2)
+	for(int c = 0; c < numCand && k < 0; c++)
 	{
-		/* round robin over the kernels that still lack two timings (the first dispatch of a volume is never timed) */
-		k = (int)(n % (unsigned)NUM_AUTO);
-		for(int tries = 0; tries < NUM_AUTO && t.samples[k] >= 2; tries++)
-			k = (k + 1) % NUM_AUTO;
+		/* round robin over the candidates that still lack two timings (the first dispatch of a volume is never timed) */
+		const int o = cand[(int)((n + (uint64_t)c) % (uint64_t)numCand)];
+		if(t.samples[o] < 2)
+			k = o;
 	}
-	else
+	if(k < 0)
 	{
 		/* hysteresis: the kernel that ran last keeps running unless another one is at least 5 % faster */
-		const int last = t.lastKernel < NUM_AUTO ? t.lastKernel : 0;
-		int best = 0;
-		for(int o = 1; o < NUM_AUTO; o++)
-			if(t.nsPerCta[o] < t.nsPerCta[best])
-				best = o;
+		int last = cand[0];
+		for(int c = 0; c < numCand; c++)
+			if(cand[c] == t.lastKernel)
+				last = cand[c];
+		int best = cand[0];
+		for(int c = 1; c < numCand; c++)
+			if(t.nsPerCta[cand[c]] < t.nsPerCta[best])
+				best = cand[c];
 		k = (best != last && t.nsPerCta[best] < 0.95 * t.nsPerCta[last]) ? best : last;
 		if((n & 63u) == 63u)
-			k = (k + 1) % NUM_AUTO;  /* keep the other kernel's estimate fresh */
+		{
+			/* keep the other candidates' estimates fresh, in turn */
+			int at = 0;
+			for(int c = 0; c < numCand; c++)
+				if(cand[c] == k)
+					at = c;
+			k = cand[(at + 1 + (int)((n >> 6) % (uint64_t)(numCand - 1))) % numCand];
+		}
 		else
 			t.lastKernel = k;
 	}
@@ -1575,7 +1592,8 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	bool ok = sync_materials(v, s);
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
 	int timingSlot = -1;
-	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
+	const bool spreadEligible = expect <= SPREAD_MAX_REQUESTS && dnb_light_spread_usable(lp.numDiffuseSamples, lp.specularBounceLimit);
+	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, spreadEligible, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
 	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself, and so does the persistent kernel
 	 * (4-byte stores as its lanes finish, but overlapped with its ray tracing: measured faster at 8 replicas than a push afterwards,
 	 * 302 vs 349 ns per 4 requests on config 3); the wavefront kernels stage locally and their rows are pushed to the peers
@@ -1593,6 +1611,8 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 		ok = ok && (P == 0 || device_reserve(v->waveCtx, (size_t)P * (dnb_wave_slot_bytes() / sizeof(uint4)), false, false, "wavefront lighting contexts"));
 		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, &work, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 16, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
 	}
+	else if(kernel == 3)
+		ok = ok && cuda_ok(dnb_launch_light_spread(&scene, v->requests.ptr, &work, std::max<uint32_t>(numCtas, 1u), &targets, s), "lighting kernel (spread)");
 	else
 		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, &work, std::max<uint32_t>(numCtas, 1u), &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
 	if(pushAfter)
@@ -1819,6 +1839,8 @@ extern "C" void DN_b200_get_stats(DNvolume* vol, DNb200stats* out)
 	v->stats.nodeSplits = v->pool.splits;
 	v->stats.nodeMerges = v->pool.merges;
 	v->stats.lightLaunchesWave = v->tuner.launches[2];
+	v->stats.lightLaunchesSpread = v->tuner.launches[3];
+	v->stats.nsPerCtaSpread = (float)v->tuner.nsPerCta[3];
 	v->stats.nsPerCtaWave = (float)v->tuner.nsPerCta[2];
 	v->stats.lastWavePasses = v->tuner.lastWavePasses;
 	if(ctx().ready && v->litCounter.ptr && DN_b200_synchronize())

@@ -120,10 +120,10 @@ struct VolumeImpl
 		cudaEvent_t begin[2] = {nullptr, nullptr}, end[2] = {nullptr, nullptr}; /* two timing slots in rotation */
 		int      slotKernel[2] = {-1, -1};   /* kernel timed in each slot, -1 = slot free */
 		uint32_t slotCtas[2] = {0, 0};
-		double   nsPerCta[3] = {0.0, 0.0, 0.0}; /* running estimate per kernel: 0 warp per request, 1 persistent, 2 wavefront */
-		uint32_t samples[3] = {0, 0, 0};
+		double   nsPerCta[4] = {0.0, 0.0, 0.0, 0.0}; /* running estimate per kernel: 0 warp per request, 1 persistent, 2 wavefront, 3 spread */
+		uint32_t samples[4] = {0, 0, 0, 0};
 		uint64_t dispatches = 0;
-		uint64_t launches[3] = {0, 0, 0};
+		uint64_t launches[4] = {0, 0, 0, 0};
 		int      lastKernel = 1;
 		uint32_t lastWavePasses = 0;
 	} tuner;

@@ -48,14 +48,54 @@ struct LightCtx
 	bool        sourceVisible;  /* visible bit of the chunk being lit, pre-dispatch (N3) */
 };
 
+/* where a ray's light goes.  The shader adds every contribution straight into the voxel's running sum (`color += ...`, LI:78,117,
+ * 123,139,143,186,197); AccSum does exactly that.  AccList keeps the addends apart instead, so that rays traced by DIFFERENT lanes
+ * (light_spread.cuh) can be replayed into the sum afterwards in the shader's order -- float addition is not associative, the order
+ * is part of the result. */
+struct AccSum
+{
+	f3 c;
+	DNB_FN void add(f3 a) { c = c + a; }
+	/* LI:101-105: a visible chunk makes the chunks it reflects visible */
+	DNB_FN void hit_tile(const DnbScene& S, uint32_t hitIndex)
+	{
+		const uint32_t bit = 1u << (hitIndex & 31u);
+		if(!(__ldcg(S.propagate + (hitIndex >> 5)) & bit))
+			atomicOr(S.propagate + (hitIndex >> 5), bit);
+	}
+};
+#define DNB_MAX_ADDENDS 4
+struct AccList
+{
+	f3 a[DNB_MAX_ADDENDS];
+	uint32_t n;
+	uint32_t tiles[DNB_MAX_ADDENDS], numTiles; /* visible-bit propagations, applied only once the voxel's rays are known to stand */
+	DNB_FN void hit_tile(const DnbScene&, uint32_t hitIndex)
+	{
+#pragma unroll
+		for(uint32_t k = 0; k < DNB_MAX_ADDENDS; k++)
+			if(k == numTiles)
+				tiles[k] = hitIndex;
+		numTiles++;
+	}
+	DNB_FN void add(f3 x)
+	{
+#pragma unroll
+		for(uint32_t k = 0; k < DNB_MAX_ADDENDS; k++) /* static indexing keeps the list in registers */
+			if(k == n)
+				a[k] = x;
+		n++;
+	}
+};
+
 DNB_FN uint32_t encode_rgba(uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
 	return ((x & 0xFFu) << 24) | ((y & 0xFFu) << 16) | ((z & 0xFFu) << 8) | (w & 0xFFu);
 }
 
 /* LI:65-80 */
-template <bool COUNT>
-DNB_FN void shadow_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, uint32_t sample, f3& color)
+template <bool COUNT, class ACC>
+DNB_FN void shadow_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, uint32_t sample, ACC& color)
 {
 	const f3 sunDir = ld3(c_light.sunDir);
 	f3 dir;
@@ -67,12 +107,12 @@ DNB_FN void shadow_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, uint32_t samp
 	f3 tmpNormal = splat3(0.0f), colorAdd;
 	float colorMult;
 	if(!trace_ray<false, COUNT>(S, cx.st, cx.lc, dir, rcp3(dir), rayPos, true, tmpNormal, colorAdd, colorMult))
-		color = color + (ld3(S.sunStrength) * colorMult + colorAdd);
+		color.add(ld3(S.sunStrength) * colorMult + colorAdd);
 }
 
 /* LI:83-146 */
-template <bool COUNT>
-DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, f3 albedo, uint32_t reflectType, f3& color)
+template <bool COUNT, class ACC>
+DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, f3 albedo, uint32_t reflectType, ACC& color)
 {
 	f3 lastPos = rayPos;
 	f3 multiplier = albedo;
@@ -88,10 +128,7 @@ DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, 
 			i3 hp = toi3(rayPos);
 			if(cx.sourceVisible && in_map_bounds(S, hp))
 			{
-				uint32_t hitIndex = (uint32_t)hp.x + S.mapSize[0] * ((uint32_t)hp.y + S.mapSize[1] * (uint32_t)hp.z);
-				uint32_t bit = 1u << (hitIndex & 31u);
-				if(!(__ldcg(S.propagate + (hitIndex >> 5)) & bit))
-					atomicOr(S.propagate + (hitIndex >> 5), bit);
+				color.hit_tile(S, (uint32_t)hp.x + S.mapSize[0] * ((uint32_t)hp.y + S.mapSize[1] * (uint32_t)hp.z));
 			}
 
 			/* LI:108-110: adjacent hit = occluded */
@@ -106,12 +143,12 @@ DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, 
 
 			if(hitMaterial.emissive)
 			{
-				color = color + ((hitAlbedo * colorMult + colorAdd) * multiplier) * albedo;
+				color.add(((hitAlbedo * colorMult + colorAdd) * multiplier) * albedo);
 				return;
 			}
 
 			f3 hitColor = hitDiffuse * hitAlbedo;
-			color = color + (hitColor * colorMult + colorAdd) * multiplier;
+			color.add((hitColor * colorMult + colorAdd) * multiplier);
 			if(hitMaterial.specular == 0.0f)
 				return;
 
@@ -122,21 +159,21 @@ DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, 
 		}
 		else if(dot3(rayDir, sunDir) > 0.99f)
 		{
-			color = color + (ld3(S.sunStrength) * colorMult + colorAdd);
+			color.add(ld3(S.sunStrength) * colorMult + colorAdd);
 			return;
 		}
 		else
 		{
 			f3 base = (reflectType == 1u) ? sky_color(S, rayDir) : ld3(S.sunStrength);
-			color = color + (base * colorMult + colorAdd) * multiplier;
+			color.add((base * colorMult + colorAdd) * multiplier);
 			return;
 		}
 	}
 }
 
 /* LI:149-203 */
-template <bool COUNT>
-DNB_FN void diffuse_ray(const DnbScene& S, LightCtx& cx, f3 normal, f3 rayPos, uint4 initialVoxel, uint32_t sample, f3& color)
+template <bool COUNT, class ACC>
+DNB_FN void diffuse_ray(const DnbScene& S, LightCtx& cx, f3 normal, f3 rayPos, uint4 initialVoxel, uint32_t sample, ACC& color)
 {
 	cx.st.vox = initialVoxel;
 	f3 hitNormal = normal;
@@ -177,7 +214,7 @@ DNB_FN void diffuse_ray(const DnbScene& S, LightCtx& cx, f3 normal, f3 rayPos, u
 			f3 through = vox_albedo(rec) * colorMult + colorAdd;
 			if(hitMaterial.emissive)
 			{
-				color = color + newColor * through;
+				color.add(newColor * through);
 				return;
 			}
 			newColor = newColor * through;
@@ -185,7 +222,7 @@ DNB_FN void diffuse_ray(const DnbScene& S, LightCtx& cx, f3 normal, f3 rayPos, u
 		else
 		{
 			float ndl = fmaxf(dot3(dir, sunDir), 0.0f);
-			color = color + (((newColor * ndl) * ld3(S.sunStrength)) * colorMult + colorAdd);
+			color.add(((newColor * ndl) * ld3(S.sunStrength)) * colorMult + colorAdd);
 			return;
 		}
 
@@ -243,6 +280,59 @@ DNB_FN uint32_t work_ctas(const DnbWork& W, uint32_t numRequests)
 
 /* registers: ptxas settles at 96 (5 CTAs = 20 warps per SM) with a few spills; both fewer registers (more warps, more spills) and
  * more registers (no spills, 16 warps) measured slower on B200 (0.49 / 0.54 ms vs 0.45 ms on config 2) */
+/* LI:266-278: clamp, quantise (round() = nearest even, N6) and pack the three lit words of a voxel */
+DNB_FN void pack_lit_words(uint4 rec, f3 specLight, f3 diffuseLight, uint32_t& w1, uint32_t& w2, uint32_t& w3)
+{
+	specLight = clamp01(specLight);
+	diffuseLight = clamp01(diffuseLight);
+	const f3 albedo = vox_albedo(rec);
+	const uint32_t wx = (uint32_t)rintf(diffuseLight.x * 65535.0f);
+	const uint32_t wy = (uint32_t)rintf(diffuseLight.y * 65535.0f);
+	const uint32_t wz = (uint32_t)rintf(diffuseLight.z * 65535.0f);
+	w1 = encode_rgba((uint32_t)rintf(albedo.x * 255.0f), (uint32_t)rintf(albedo.y * 255.0f), (uint32_t)rintf(albedo.z * 255.0f), (uint32_t)rintf(specLight.x * 255.0f));
+	w2 = encode_rgba((uint32_t)rintf(specLight.y * 255.0f), (uint32_t)rintf(specLight.z * 255.0f), (wx >> 8) & 0xFFu, wx & 0xFFu);
+	w3 = encode_rgba((wy >> 8) & 0xFFu, wy & 0xFFu, (wz >> 8) & 0xFFu, wz & 0xFFu);
+}
+
+/* the whole of one shader invocation after its set-up (LI:234-278), every ray traced by THIS thread in the shader's order */
+template <bool COUNT>
+DNB_FN void light_voxel(const DnbScene& S, LightCtx& cx, uint4 rec, const DnbMaterial& material, f3 rayPos, float indirectSamples, uint32_t& w1, uint32_t& w2, uint32_t& w3)
+{
+	const f3 normal = vox_normal(rec);
+	const f3 albedo = vox_albedo(rec);
+	AccSum spec, diff;
+	spec.c = splat3(0.0f);
+	diff.c = splat3(0.0f);
+
+	/* LI:239-251 */
+	const f3 viewDir = rayPos - ld3(c_light.camPos);
+	if(material.specular > 0.0f && dot3(viewDir, normal) < 0.0f && material.reflectType <= 1u)
+	{
+		const f3 reflected = reflect3(normalize3(viewDir), normal);
+		for(int i = 0; i < 15; i++)
+		{
+			f3 specDir = normalize3(reflected * (float)material.shininess + ld3(c_spherePoints[i])) + DNB_EPSILON;
+			specular_ray<COUNT>(S, cx, rayPos, specDir, albedo, material.reflectType, spec);
+		}
+		spec.c = div3(spec.c, 15.0f);
+	}
+
+	/* LI:254-264 */
+	if(material.specular < 1.0f)
+	{
+		const f3 ambient = ld3(S.ambient);
+		for(uint32_t i = 0; i < c_light.numDiffuseSamples; i++)
+		{
+			diff.c = diff.c + ambient;
+			diffuse_ray<COUNT>(S, cx, normal + DNB_EPSILON, rayPos, rec, i, diff);
+			shadow_ray<COUNT>(S, cx, rayPos, i, diff);
+		}
+		const float denom = indirectSamples + (float)c_light.numDiffuseSamples;
+		diff.c = div3(vox_diffuse(rec) * indirectSamples + diff.c, denom);
+	}
+	pack_lit_words(rec, spec.c, diff.c, w1, w2, w3);
+}
+
 template <bool COUNT>
 DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ requests, uint32_t r, uint32_t warp, uint32_t lane, const DnbStagingTargets& T, DnbSlot* s_slot);
 
@@ -303,7 +393,6 @@ DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ reques
 
 	const uint4 rec = __ldg(S.records + (slot.voxelBase + voxNum));
 	const f3 normal = vox_normal(rec);
-	const f3 albedo = vox_albedo(rec);
 	const DnbMaterial material = load_material(S, vox_material(rec));
 
 	const uint32_t ns = slot.numSamples; /* pre-dispatch value for every group of the chunk (N2) */
@@ -315,48 +404,9 @@ DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ reques
 	f3 rayPos = (tof3(chunkPos) * 0.125f + tof3(mapPos)) + 0.0625f;
 	rayPos = rayPos + normal * (0.0625f - DNB_EPSILON);
 
-	f3 specLight = splat3(0.0f);
-	f3 diffuseLight = splat3(0.0f);
-
-	/* LI:239-251 */
-	const f3 viewDir = rayPos - ld3(c_light.camPos);
-	if(material.specular > 0.0f && dot3(viewDir, normal) < 0.0f && material.reflectType <= 1u)
-	{
-		const f3 reflected = reflect3(normalize3(viewDir), normal);
-		for(int i = 0; i < 15; i++)
-		{
-			f3 specDir = normalize3(reflected * (float)material.shininess + ld3(c_spherePoints[i])) + DNB_EPSILON;
-			specular_ray<COUNT>(S, cx, rayPos, specDir, albedo, material.reflectType, specLight);
-		}
-		specLight = div3(specLight, 15.0f);
-	}
-
-	/* LI:254-264 */
-	if(material.specular < 1.0f)
-	{
-		const f3 ambient = ld3(S.ambient);
-		for(uint32_t i = 0; i < c_light.numDiffuseSamples; i++)
-		{
-			diffuseLight = diffuseLight + ambient;
-			diffuse_ray<COUNT>(S, cx, normal + DNB_EPSILON, rayPos, rec, i, diffuseLight);
-			shadow_ray<COUNT>(S, cx, rayPos, i, diffuseLight);
-		}
-		const float denom = indirectSamples + (float)c_light.numDiffuseSamples;
-		diffuseLight = div3(vox_diffuse(rec) * indirectSamples + diffuseLight, denom);
-	}
-
-	specLight = clamp01(specLight);
-	diffuseLight = clamp01(diffuseLight);
-
-	/* LI:271-278; round() = nearest even (N6) */
-	const uint32_t wx = (uint32_t)rintf(diffuseLight.x * 65535.0f);
-	const uint32_t wy = (uint32_t)rintf(diffuseLight.y * 65535.0f);
-	const uint32_t wz = (uint32_t)rintf(diffuseLight.z * 65535.0f);
-
-	stage_words(T, at,
-	            encode_rgba((uint32_t)rintf(albedo.x * 255.0f), (uint32_t)rintf(albedo.y * 255.0f), (uint32_t)rintf(albedo.z * 255.0f), (uint32_t)rintf(specLight.x * 255.0f)),
-	            encode_rgba((uint32_t)rintf(specLight.y * 255.0f), (uint32_t)rintf(specLight.z * 255.0f), (wx >> 8) & 0xFFu, wx & 0xFFu),
-	            encode_rgba((wy >> 8) & 0xFFu, wy & 0xFFu, (wz >> 8) & 0xFFu, wz & 0xFFu));
+	uint32_t w1, w2, w3;
+	light_voxel<COUNT>(S, cx, rec, material, rayPos, indirectSamples, w1, w2, w3);
+	stage_words(T, at, w1, w2, w3);
 
 	if(COUNT)
 	{
@@ -458,6 +508,7 @@ __global__ void dn_merge_visible_peers_kernel(DnbPeerTable T, uint32_t* __restri
 
 #include "light_flat.cuh"
 #include "light_wave.cuh"
+#include "light_spread.cuh"
 
 static DnbFlatTuning g_flatTuning = {0, 0, 0};
 

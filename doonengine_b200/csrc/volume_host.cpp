@@ -12,9 +12,6 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
-#if defined(__linux__)
-#include <sys/mman.h>
-#endif
 
 extern "C" void (*g_DN_message_callback)(DNmessageType, DNmessageSeverity, const char*) = nullptr;
 
@@ -39,20 +36,6 @@ void touch_tile(VolumeImpl* v, size_t mapIndex)
 		return;
 	v->touchedFlag[mapIndex] = 1;
 	v->touched.push_back((uint32_t)mapIndex);
-}
-
-/* The chunk array of a large map is hundreds of megabytes to gigabytes, and edits land all over it: with 4 KB pages every access
- * also misses the TLB.  Ask for huge pages where the kernel leaves that to madvise (a hint; failure is harmless). */
-static void advise_huge(void* p, size_t bytes)
-{
-#if defined(__linux__)
-	const uintptr_t a = ((uintptr_t)p + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
-	const uintptr_t e = ((uintptr_t)p + bytes) & ~(((uintptr_t)2 << 20) - 1);
-	if(e > a)
-		madvise((void*)a, (size_t)(e - a), MADV_HUGEPAGE);
-#else
-	(void)p; (void)bytes;
-#endif
 }
 
 /* voxel.c:1353-1363; numVoxelsGpu deliberately survives, as upstream */
@@ -97,10 +80,6 @@ extern "C" DNvolume* DN_create_volume(DNuvec3 mapSize, unsigned int minChunks)
 	vol->mapSize = mapSize;
 	vol->map = (DNchunkHandle*)DN_MALLOC(sizeof(DNchunkHandle) * (tiles ? tiles : 1));
 	vol->chunks = (DNchunk*)DN_MALLOC(sizeof(DNchunk) * numChunks);
-	if(vol->chunks)
-		advise_huge(vol->chunks, sizeof(DNchunk) * numChunks);
-	if(vol->map)
-		advise_huge(vol->map, sizeof(DNchunkHandle) * (tiles ? tiles : 1));
 	vol->materials = (DNmaterial*)DN_MALLOC(sizeof(DNmaterial) * DN_MAX_MATERIALS);
 	vol->lightingRequests = (GLuint*)DN_MALLOC(sizeof(GLuint) * numChunks);
 	vol->gpuVoxelLayout = NULL; /* mirrored on demand, see DN_b200 docs */
@@ -537,8 +516,6 @@ extern "C" bool DN_set_max_chunks(DNvolume* vol, size_t num)
 	if(num == 0)
 		num = 1;
 	DNchunk* grown = (DNchunk*)DN_REALLOC(vol->chunks, sizeof(DNchunk) * num);
-	if(grown)
-		advise_huge(grown, sizeof(DNchunk) * num);
 	if(!grown)
 	{
 		report(DN_MESSAGE_CPU_MEMORY, DN_MESSAGE_ERROR, "failed to reallocate memory for chunks");

@@ -114,6 +114,9 @@ typedef struct DNb200stats
 	uint64_t nodeSplits, nodeMerges;                        /* record-pool allocator: buddy splits / merges since creation */
 	uint64_t usedNodes, freeNodes;                          /* record-pool nodes now */
 	uint64_t recordTop;                                     /* records of the pool handed out to the allocator (multiple of 512) */
+	uint64_t lightLaunchesSpread;                           /* lighting dispatches run by the one-warp-per-voxel kernel (small dispatches) */
+	float    nsPerCtaSpread;                                /* auto mode: its time per 4 requests */
+	uint32_t pad1;
 } DNb200stats;
 void DN_b200_get_stats(DNvolume* vol, DNb200stats* out); /* synchronises (reads the device-side lit counter) */
 void DN_b200_enable_timing(bool enable);

@@ -18,11 +18,12 @@ pytestmark = pytest.mark.gpu
 W, H, FRAMES = 320, 192, 4
 
 
-@pytest.fixture(autouse=True, params=["flat", "warp", "wave"])
+@pytest.fixture(autouse=True, params=["flat", "warp", "wave", "spread"])
 def light_kernel(request, dn):
-    """every test of this module runs against all three lighting kernels: the persistent state machine (light_flat.cuh), the
-    one-warp-per-request kernel (light.cu) and the wavefront pair (light_wave.cuh); their results must be the same bits."""
-    dn.lib().DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3}[request.param])
+    """every test of this module runs against all four lighting kernels: the persistent state machine (light_flat.cuh), the
+    one-warp-per-request kernel (light.cu), the wavefront pair (light_wave.cuh) and the one-warp-per-voxel kernel for small dispatches
+    (light_spread.cuh); their results must be the same bits."""
+    dn.lib().DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3, "spread": 4}[request.param])
     yield request.param
     dn.lib().DN_b200_set_light_kernel(2)  # back to auto
 
@@ -524,7 +525,7 @@ def test_kernels_agree_on_sparse_map_with_streamed_pool(dn, light_kernel):
             staged = {}
             L.DN_b200_set_light_kernel(0)
             assert L.DN_b200_light_compute(e.vol, 1, 1000, 1.0 + k / 60.0)  # sizes the staging array for this frame's request count
-            for name, mode, slots in (("warp", 0, 0), ("flat", 1, 0), ("wave-all", 3, 1 << 22), ("wave-4k", 3, 4096), ("wave-640", 3, 640)):
+            for name, mode, slots in (("warp", 0, 0), ("flat", 1, 0), ("spread", 4, 0), ("wave-all", 3, 1 << 22), ("wave-4k", 3, 4096), ("wave-640", 3, 640)):
                 L.DN_b200_set_light_kernel(mode)
                 if mode == 3:
                     L.DN_b200_set_wave_slots(slots)

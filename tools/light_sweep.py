@@ -38,7 +38,7 @@ variants = [(n, (24, 28, 16) if n == "flat" else None) for n in names]
 out = []
 k = 0
 for name, knobs in variants:
-    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3}[name])
+    L.DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3, "spread": 4}[name])
     if knobs:
         L.DN_b200_set_flat_tuning(*knobs)
     times, dtimes = [], []
