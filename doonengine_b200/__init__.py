@@ -191,6 +191,7 @@ _PROTOTYPES = {
     "DN_b200_set_voxels": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p]),
     "DN_b200_lighting_request_count": (C.c_size_t, [C.POINTER(DNvolume)]),
     "DN_b200_set_exact_sync": (None, [C.POINTER(DNvolume), C.c_bool]),
+    "DN_b200_set_max_frames_in_flight": (None, [C.POINTER(DNvolume), C.c_int]),
     "DN_b200_mirror_voxel_layout": (C.c_bool, [C.POINTER(DNvolume)]),
     "DN_b200_step_map_batch": (C.c_size_t, [C.POINTER(DNvolume), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "DN_b200_set_wave_slots": (None, [C.c_uint32]),

@@ -138,6 +138,11 @@ void device_destroy(VolumeImpl* v)
 	device_free(v->blockCounts); device_free(v->blockOffsets); device_free(v->scalars); device_free(v->forcedList); device_free(v->waveCtx); device_free(v->pickRays); device_free(v->pickHits); device_free(v->blobs[0]); device_free(v->blobs[1]); device_free(v->litCounter);
 	device_free(v->mailbox); device_free(v->barrierStatus);
 	v->peerAttached = false;
+	for(int k = 0; k < 4; k++)
+	{
+		if(v->frameDone[k]) cudaEventDestroy(v->frameDone[k]);
+		v->frameDone[k] = nullptr;
+	}
 	for(int slot = 0; slot < 2; slot++)
 	{
 		if(v->tuner.begin[slot]) cudaEventDestroy(v->tuner.begin[slot]);
@@ -1274,6 +1279,13 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 		report(DN_MESSAGE_GPU_MEMORY, DN_MESSAGE_ERROR, "DN_draw: cubemap skies are not supported by the CUDA back end; using the sky gradient");
 
 	cudaStream_t s = ctx().stream();
+	/* frame pacing (engine.h): the draw of the frame maxFramesInFlight frames back -- and so everything queued before it -- has finished */
+	if(v->maxFramesInFlight > 0 && v->framesCommitted >= (uint64_t)v->maxFramesInFlight)
+	{
+		cudaEvent_t ev = v->frameDone[(v->framesCommitted - (uint64_t)v->maxFramesInFlight) & 3u];
+		if(ev)
+			cuda_ok(cudaEventSynchronize(ev), "frame pacing");
+	}
 	if(fb->readPending)
 	{
 		/* pixels of the previous frame may still be on their way to the host */
@@ -1332,6 +1344,14 @@ extern "C" void DN_draw(DNvolume* vol, GLuint outputTexture, DNmat4 view, DNmat4
 		cuda_ok(dnb_launch_peer_or_visible(&v->peers, v->visible.ptr, (uint32_t)((num_tiles(vol) + 31) / 32), s), "visible merge");
 		v->peerMergeUnfenced = true;
 	}
+
+	/* frame pacing: the end of this frame's draw (and with it of everything queued before it: the previous frame's lighting) */
+	cudaEvent_t& done = v->frameDone[v->framesCommitted & 3u];
+	if(!done)
+		cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+	if(done)
+		cudaEventRecord(done, s);
+	v->framesCommitted++;
 }
 
 /* which lighting kernel runs: 0 = one warp per request (light.cu), 1 = persistent state machine (light_flat.cuh), 2 = whichever
@@ -1786,6 +1806,11 @@ extern "C" size_t DN_b200_lighting_request_count(DNvolume* vol)
 extern "C" void DN_b200_set_exact_sync(DNvolume* vol, bool exact)
 {
 	impl_of(vol)->exactSync = exact;
+}
+
+extern "C" void DN_b200_set_max_frames_in_flight(DNvolume* vol, int frames)
+{
+	impl_of(vol)->maxFramesInFlight = frames < 0 ? 0 : (frames > 3 ? 3 : frames);
 }
 
 extern "C" bool DN_b200_enable_counters(DNvolume* vol, bool enable)

@@ -109,6 +109,11 @@ struct VolumeImpl
 	size_t requestsValid = 0;                  /* exact length, once known (0 after a sync that did not read) */
 	size_t lastExactCount = 0;                 /* the most recent exact length seen: sizes grids while the current one is still in flight */
 	bool   exactSync = false;                  /* DN_sync_gpu waits for the exact length (numLightingRequests valid at return, as upstream) */
+	/* frame pacing: nothing in the frame calls waits for the device any more, so the host could queue arbitrarily many frames ahead;
+	 * DN_draw therefore waits until the draw of the frame `maxFramesInFlight` frames back (and everything queued before it) has finished */
+	cudaEvent_t frameDone[4] = {nullptr, nullptr, nullptr, nullptr};
+	uint64_t    framesCommitted = 0;       /* draws queued so far */
+	int         maxFramesInFlight = 2;
 	size_t stagedBound = 0;                    /* requestBound of the last compute phase (sizes the staging array and the commit grid) */
 	size_t stagedRequests = 0;                 /* exact length used by the last compute phase, where it was needed (collective sharding), else 0 */
 	int    shardRank = 0, shardWorld = 1;

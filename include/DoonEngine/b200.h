@@ -90,6 +90,10 @@ void*  DN_b200_array_device_ptr(DNvolume* vol, DNb200array which);
  *   DN_b200_set_exact_sync(vol, true)  restores upstream's contract: every reading DN_sync_gpu waits, the field is exact at return ---- */
 size_t DN_b200_lighting_request_count(DNvolume* vol);
 void   DN_b200_set_exact_sync(DNvolume* vol, bool exact);
+/* frame pacing: with no call of the frame loop waiting for the device, DN_draw holds the host back until the draw of the frame
+ * `frames` frames earlier -- and so everything queued before it -- has finished (default 2: the device never runs dry, latency stays
+ * bounded); 0 = no limit, at most 3 */
+void   DN_b200_set_max_frames_in_flight(DNvolume* vol, int frames);
 
 /* ---- instrumentation ---- */
 typedef struct DNb200counters { uint64_t rays, tiles, chunks, voxelSteps, records, voxelsLit, pixels; } DNb200counters;
