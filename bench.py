@@ -350,7 +350,13 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         scenes.build_native(e, scene, tiles, **camera)
     else:
         chunks, camera = make_chunks(scene, tiles) if scene != "demo" else ([], {})
-        e = build_engine(dn.Engine, scene, tiles, chunks, camera)
+        kw = {}
+        if config == "c4":
+            # the edit stream creates a chunk for (nearly) every voxel it sets in the air: the chunk array is sized for the whole run through
+            # the API's own minChunks parameter (voxel.h: DN_create_volume), as an application that knows its edit rate would -- doubling a
+            # 0.4 -> 0.8 -> 1.5 GB array by realloc in the middle of the timed frames (voxel.c:1015) measures the allocator, not the path
+            kw["min_chunks"] = len(chunks) + (8 + warmup + 2 * steps + 2) * EDITS_PER_FRAME // 2 + 4096
+        e = build_engine(dn.Engine, scene, tiles, chunks, camera, **kw)
     e.sync(dn.DN_WRITE, 1)
     e.synchronize()
     t_build = time.perf_counter() - t_build

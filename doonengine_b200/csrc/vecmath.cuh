@@ -11,7 +11,7 @@
 struct f3 { float x, y, z; };
 struct i3 { int x, y, z; };
 
-/* A host harness (tools/proto) may define DNB_FN as __host__ __device__ to run the traversal code on the CPU; the read-only-load and
+/* A host harness (tests/csrc/ray_step_harness.cu) may define DNB_FN as __host__ __device__ to run the traversal code on the CPU; the read-only-load and
  * bit intrinsics go through these wrappers for the same reason (device code is unchanged by them). */
 #ifndef DNB_FN
 #define DNB_FN __device__ __forceinline__

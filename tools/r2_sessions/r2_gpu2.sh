@@ -1,8 +1,8 @@
 #!/bin/bash
 # round 2, GPU session 2: diagnostics of the sparse-map parity failure, the rest of the parity suite, full-pass captures of both step kernels
 mkdir -p gpurun_out
-timeout 600 python tools/r2_diag_sparse.py sparse 20,20,20 > gpurun_out/g2_diag_sparse.log 2>&1
-timeout 600 python tools/r2_diag_sparse.py dense 8,8,8 > gpurun_out/g2_diag_dense.log 2>&1
+timeout 600 python tools/r2_sessions/r2_diag_sparse.py sparse 20,20,20 > gpurun_out/g2_diag_sparse.log 2>&1
+timeout 600 python tools/r2_sessions/r2_diag_sparse.py dense 8,8,8 > gpurun_out/g2_diag_dense.log 2>&1
 tail -c 3000 gpurun_out/g2_diag_sparse.log
 timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_parity_gpu.py::test_sparse_balls_against_oracle 2>&1 | tail -25 > gpurun_out/g2_pytest.log
 tail -5 gpurun_out/g2_pytest.log
