@@ -46,14 +46,7 @@ struct LightCtx
 	DnbCounters lc;
 	bool        firstSample;    /* LI:62 */
 	bool        sourceVisible;  /* visible bit of the chunk being lit, pre-dispatch (N3) */
-	uint32_t    ownSlot, ownMapIndex; /* slot + 1 and tile of the chunk being lit: the start hint of every ray that leaves the voxel (trace.cuh RayState) */
 };
-
-DNB_FN void hint_own_chunk(LightCtx& cx)
-{
-	cx.st.startSlot = cx.ownSlot;
-	cx.st.startMapIndex = cx.ownMapIndex;
-}
 
 /* where a ray's light goes.  The shader adds every contribution straight into the voxel's running sum (`color += ...`, LI:78,117,
  * 123,139,143,186,197); AccSum does exactly that.  AccList keeps the addends apart instead, so that rays traced by DIFFERENT lanes
@@ -113,7 +106,6 @@ DNB_FN void shadow_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, uint32_t samp
 
 	f3 tmpNormal = splat3(0.0f), colorAdd;
 	float colorMult;
-	hint_own_chunk(cx);
 	if(!trace_ray<false, COUNT>(S, cx.st, cx.lc, dir, rcp3(dir), rayPos, true, tmpNormal, colorAdd, colorMult))
 		color.add(ld3(S.sunStrength) * colorMult + colorAdd);
 }
@@ -125,7 +117,6 @@ DNB_FN void specular_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, f3 rayDir, 
 	f3 lastPos = rayPos;
 	f3 multiplier = albedo;
 	const f3 sunDir = ld3(c_light.sunDir);
-	hint_own_chunk(cx); /* (later segments start where the previous one hit: trace_ray leaves that hint itself) */
 
 	for(uint32_t i = 0; i < c_light.specularBounceLimit; i++)
 	{
@@ -185,7 +176,6 @@ template <bool COUNT, class ACC>
 DNB_FN void diffuse_ray(const DnbScene& S, LightCtx& cx, f3 normal, f3 rayPos, uint4 initialVoxel, uint32_t sample, ACC& color)
 {
 	cx.st.vox = initialVoxel;
-	hint_own_chunk(cx);
 	f3 hitNormal = normal;
 	DnbMaterial hitMaterial;
 	hitMaterial.specular = 0.0f;
@@ -397,8 +387,6 @@ DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ reques
 	cx.lc = DnbCounters{0, 0, 0, 0, 0, 0, 0};
 	cx.firstSample = false;
 	cx.sourceVisible = (__ldg(S.visible + (mapIndex >> 5)) >> (mapIndex & 31u)) & 1u;
-	cx.ownSlot = slotId + 1u;
-	cx.ownMapIndex = mapIndex;
 
 	const i3 chunkPos = {local & 7, (local >> 3) & 7, local >> 6};
 	const i3 mapPos = {slot.pos[0], slot.pos[1], slot.pos[2]};

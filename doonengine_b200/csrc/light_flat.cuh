@@ -63,12 +63,10 @@ struct FlatLane
 	i3       cp;
 	f3       cside, cpos, tile;
 	float    ctLast;
-	uint32_t slotIndex;      /* S.slots + slotIndex */
+	const DnbSlot* slot;
 	uint32_t wordIdx, word, cguard, mapIndex;
 	uint32_t cbias, coffp;   /* exact chunk cull (trace.cuh cull_offsets): cp is shifted by the offsets in coffp */
 	bool     chunkOpaque;    /* every material of the chunk is opaque (layout.h DNB_BBOX_OPAQUE): a set voxel bit is an opaque hit */
-	uint32_t hintSlot, hintMapIndex; /* start hint of the NEXT segment (trace.cuh RayState.startSlot): slot + 1 of the tile it starts in, 0 = unknown */
-	uint32_t ownSlot, ownMapIndex;   /* the chunk being lit: the start hint of every ray that leaves the voxel */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -92,61 +90,10 @@ DNB_FN void flat_start_ray(FlatLane& L, uint32_t& state)
 	state = ST_TILE;
 }
 
-/* the tile L.m.pos (flat index L.mapIndex) holds chunk slot `slotIndex`: SH:443-445, then step_chunk's prologue */
-DNB_FN void flat_enter_chunk(const DnbScene& S, FlatLane& L, uint32_t& state, uint32_t slotIndex)
-{
-	Dda& m = L.m;
-	L.slotIndex = slotIndex;
-	const DnbSlot* slot = S.slots + slotIndex;
-	L.tile = tof3(m.pos);
-	const f3 entry = L.pos + L.dir * (L.tLast - DNB_EPSILON);
-	f3 cpos = (entry - L.tile) * 8.0f;
-	cpos = min3v(max3v(cpos, splat3(DNB_EPSILON)), splat3(8.0f - DNB_EPSILON));
-	L.cpos = cpos;
-	/* init_dda(rayDir, invRayDir, cpos, c): delta and step equal the tile level's */
-	const f3 cell = floor3(cpos);
-	L.cp = toi3(cell);
-	const f3 sg = mk3(sgn(L.dir.x), sgn(L.dir.y), sgn(L.dir.z));
-	const f3 t = sg * (cell - cpos) + sg * 0.5f;
-	L.cside = (t + 0.5f) * m.delta;
-	L.ctLast = 0.0f;
-	L.cguard = 0;
-	/* both loads that depend on the slot index leave together (the entry cell's mask word and the bounding-box word, whose top
-	 * bit says whether every material of the chunk is opaque: trace.cuh) */
-	L.wordIdx = ((uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z)) >> 5;
-	L.word = __ldg(slot->mask + L.wordIdx);
-	const uint32_t bbox = __ldg(&slot->bbox);
-	L.chunkOpaque = (bbox & DNB_BBOX_OPAQUE) != 0u;
-	L.cbias = 0;
-	L.coffp = 0;
-	if(L.st.lastVoxID == 255u)
-		L.coffp = cull_offsets(bbox, m.step, L.cp, L.cbias);
-	state = ST_VOX;
-}
-
 /* one iteration of trace_ray's phase-A loop */
 DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 {
 	Dda& m = L.m;
-	if(L.hintSlot != 0u)
-	{
-		/* start hint (trace.cuh RayState.startSlot): if the ray's first cell is the hinted tile, its chunk is entered without looking at
-		 * the occupancy word or the tile -> slot table; the guard and the tripped test are those of the ordinary iteration */
-		const uint32_t hint = L.hintSlot;
-		L.hintSlot = 0u;
-		if(in_map_bounds(S, m.pos) && (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z) == L.hintMapIndex)
-		{
-			if(++L.guard > S.maxMapSteps || L.st.tripped)
-			{
-				L.st.tripped = true;
-				state = ST_END;
-				return;
-			}
-			L.mapIndex = L.hintMapIndex;
-			flat_enter_chunk(S, L, state, hint - 1u);
-			return;
-		}
-	}
 	if((uint32_t)((m.pos.x ^ L.blk.x) | (m.pos.y ^ L.blk.y) | (m.pos.z ^ L.blk.z)) > 3u)
 	{
 		if(!in_map_bounds(S, m.pos) ||
@@ -183,8 +130,33 @@ DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 	const uint32_t bit = (uint32_t)(m.pos.x & 3) | ((uint32_t)(m.pos.y & 3) << 2) | ((uint32_t)(m.pos.z & 3) << 4);
 	if((L.occWord >> bit) & 1ull)
 	{
+		/* resident chunk: SH:443-445, then step_chunk's prologue */
 		L.mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
-		flat_enter_chunk(S, L, state, __ldg(S.tileSlot + L.mapIndex) - 1u);
+		L.slot = S.slots + (__ldg(S.tileSlot + L.mapIndex) - 1u);
+		L.tile = tof3(m.pos);
+		const f3 entry = L.pos + L.dir * (L.tLast - DNB_EPSILON);
+		f3 cpos = (entry - L.tile) * 8.0f;
+		cpos = min3v(max3v(cpos, splat3(DNB_EPSILON)), splat3(8.0f - DNB_EPSILON));
+		L.cpos = cpos;
+		/* init_dda(rayDir, invRayDir, cpos, c): delta and step equal the tile level's */
+		const f3 cell = floor3(cpos);
+		L.cp = toi3(cell);
+		const f3 sg = mk3(sgn(L.dir.x), sgn(L.dir.y), sgn(L.dir.z));
+		const f3 t = sg * (cell - cpos) + sg * 0.5f;
+		L.cside = (t + 0.5f) * m.delta;
+		L.ctLast = 0.0f;
+		L.cguard = 0;
+		/* both loads that depend on the slot index leave together (the entry cell's mask word and the bounding-box word, whose top
+		 * bit says whether every material of the chunk is opaque: trace.cuh) */
+		L.wordIdx = ((uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z)) >> 5;
+		L.word = __ldg(L.slot->mask + L.wordIdx);
+		const uint32_t bbox = __ldg(&L.slot->bbox);
+		L.chunkOpaque = (bbox & DNB_BBOX_OPAQUE) != 0u;
+		L.cbias = 0;
+		L.coffp = 0;
+		if(L.st.lastVoxID == 255u)
+			L.coffp = cull_offsets(bbox, m.step, L.cp, L.cbias);
+		state = ST_VOX;
 		return;
 	}
 	iterate_dda(m, L.tLast);
@@ -213,14 +185,13 @@ DNB_FN void flat_vox_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 	if((local >> 5) != L.wordIdx)
 	{
 		L.wordIdx = local >> 5;
-		L.word = __ldg(S.slots[L.slotIndex].mask + L.wordIdx);
+		L.word = __ldg(L.slot->mask + L.wordIdx);
 	}
 
 	if(((L.word >> (local & 31u)) & 1u) && !L.ignoreFirst)
 	{
-		const DnbSlot* slot = S.slots + L.slotIndex;
-		const uint32_t rel = (uint32_t)__ldg(slot->prefix + L.wordIdx) + __popc(L.word & ((1u << (local & 31u)) - 1u));
-		const uint4 rec = __ldg(S.records + (__ldg(&slot->voxelBase) + rel));
+		const uint32_t rel = (uint32_t)__ldg(L.slot->prefix + L.wordIdx) + __popc(L.word & ((1u << (local & 31u)) - 1u));
+		const uint4 rec = __ldg(S.records + (__ldg(&L.slot->voxelBase) + rel));
 		L.st.vox = rec;
 		DnbMaterial material;
 		material.opacity = 1.0f;
@@ -235,8 +206,6 @@ DNB_FN void flat_vox_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 			L.st.hitMapIndex = L.mapIndex;
 			L.st.hitLocalIndex = local;
 			L.st.hitRecord = rel;
-			L.hintSlot = L.slotIndex + 1u; /* a segment continuing from here starts inside this chunk */
-			L.hintMapIndex = L.mapIndex;
 			L.hit = true;
 			state = ST_END;
 			return;
@@ -314,8 +283,6 @@ DNB_FN bool flat_start_spec(FlatLane& L, const DnbMaterial& material)
 	L.kind = RAY_SPEC;
 	L.seg = 0;
 	L.pos = L.origin;
-	L.hintSlot = L.ownSlot;
-	L.hintMapIndex = L.ownMapIndex;
 	L.pa = L.origin;           /* lastPos */
 	L.pb = vox_albedo(L.rec);  /* multiplier */
 	L.reflectType = material.reflectType;
@@ -363,8 +330,6 @@ DNB_FN bool flat_start_shadow(FlatLane& L)
 		dir = normalize3(sunDir * c_light.shadowSoftness + ld3(c_light.shadowBall[L.idx])) + DNB_EPSILON;
 	L.kind = RAY_SHADOW;
 	L.pos = L.origin;
-	L.hintSlot = L.ownSlot;
-	L.hintMapIndex = L.ownMapIndex;
 	L.dir = dir;
 	return true;
 }
@@ -379,8 +344,6 @@ DNB_FN bool flat_start_sample(const DnbScene& S, FlatLane& L)
 	L.pa = splat3(1.0f); /* newColor */
 	L.pb = splat3(0.0f); /* lastDir */
 	L.pos = L.origin;
-	L.hintSlot = L.ownSlot;
-	L.hintMapIndex = L.ownMapIndex;
 	if(!flat_start_diffuse_segment(S, L))
 		flat_start_shadow(L);
 	return true;
@@ -546,9 +509,6 @@ DNB_FN bool flat_setup_voxel(const DnbScene& S, const DnbStagingTargets& T, cons
 	}
 
 	ray_state_reset(L.st);
-	L.ownSlot = slotId + 1u;
-	L.ownMapIndex = mapIndex;
-	L.hintSlot = 0;
 	L.sourceVisible = (__ldg(S.visible + (mapIndex >> 5)) >> (mapIndex & 31u)) & 1u;
 	const i3 chunkPos = {local & 7, (local >> 3) & 7, local >> 6};
 	const i3 mapPos = {__ldg(&slot->pos[0]), __ldg(&slot->pos[1]), __ldg(&slot->pos[2])};

@@ -68,8 +68,6 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbS
 		cx.lc = DnbCounters{0, 0, 0, 0, 0, 0, 0};
 		cx.firstSample = indirectSamples == 0.0f;
 		cx.sourceVisible = (__ldg(S.visible + (mapIndex >> 5)) >> (mapIndex & 31u)) & 1u;
-		cx.ownSlot = slotId + 1u;
-		cx.ownMapIndex = mapIndex;
 
 		const f3 viewDir = rayPos - ld3(c_light.camPos);
 		const bool specular = material.specular > 0.0f && dot3(viewDir, normal) < 0.0f && material.reflectType <= 1u;

@@ -32,11 +32,6 @@ struct RayState
 	uint4    vox;            /* last record fetched by any ray of this thread */
 	bool     tripped;        /* a loop guard fired; all later rays of the thread miss (oracle.h N11) */
 	uint32_t hitMapIndex, hitLocalIndex, hitRecord; /* where the last opaque hit happened */
-	/* start hint: "the tile startMapIndex holds chunk slot startSlot - 1" (0 = no hint).  Every lighting ray starts inside a voxel --
-	 * the voxel being lit, or the one the previous segment hit -- so the caller usually knows the first tile's slot already; a ray
-	 * whose first cell is that tile skips the occupancy word and the tile -> slot lookup (two dependent loads).  Purely a shortcut:
-	 * a hint whose tile is not the ray's first cell is ignored, and a tile determines its slot, so a stale hint can never mislead. */
-	uint32_t startSlot, startMapIndex;
 };
 
 DNB_FN void ray_state_reset(RayState& st)
@@ -46,7 +41,6 @@ DNB_FN void ray_state_reset(RayState& st)
 	st.vox = make_uint4(0, 0, 0, 0);
 	st.tripped = false;
 	st.hitMapIndex = st.hitLocalIndex = st.hitRecord = 0;
-	st.startSlot = st.startMapIndex = 0;
 }
 
 /* record decode, SH:236-256 (constants are the shader's, not exactly 1/255 and 1/65535) */
@@ -201,29 +195,12 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 	i3 blk = {0x40000000, 0x40000000, 0x40000000}; /* base tile of the cached occupancy block (never a real one) */
 	unsigned long long occWord = 0;
 
-	/* the start hint (RayState): valid if the ray's first cell is the hinted tile */
-	uint32_t hintSlot = COUNT ? 0u : st.startSlot;
-	st.startSlot = 0;
-	if(hintSlot != 0u && !(in_map_bounds(S, m.pos) && (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z) == st.startMapIndex))
-		hintSlot = 0u;
-
 	for(;;)
 	{
 		/* ---- phase A: advance tile by tile to the next resident chunk.  Kept as its own loop ("while-while"
 		 * traversal) so that the lanes of a warp search together and then cross their chunks together, instead of
 		 * every lane that reaches a chunk stalling the lanes that are still stepping over empty tiles. ---- */
 		bool found = false;
-		if(hintSlot != 0u)
-		{
-			/* the first cell holds the hinted chunk: what the loop below would find after loading the occupancy word */
-			if(++guard > S.maxMapSteps || st.tripped)
-			{
-				st.tripped = true;
-				break;
-			}
-			found = true;
-		}
-		else
 		for(;;)
 		{
 			if((uint32_t)((m.pos.x ^ blk.x) | (m.pos.y ^ blk.y) | (m.pos.z ^ blk.z)) > 3u)
@@ -279,9 +256,7 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 		/* ---- phase B: cross the resident chunk voxel by voxel ---- */
 		{
 			const uint32_t mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
-			const uint32_t slotIndex = (hintSlot != 0u ? hintSlot : DNB_LDG(S.tileSlot + mapIndex)) - 1u;
-			hintSlot = 0u;
-			const DnbSlot* slot = S.slots + slotIndex;
+			const DnbSlot* slot = S.slots + (DNB_LDG(S.tileSlot + mapIndex) - 1u);
 			DNB_COUNT(chunks);
 
 			/* SH:443-445: entry point in chunk-local voxel units */
@@ -349,8 +324,6 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 						st.hitMapIndex = mapIndex;
 						st.hitLocalIndex = local;
 						st.hitRecord = rel;
-						st.startSlot = slotIndex + 1u; /* a segment continuing from here starts inside this chunk */
-						st.startMapIndex = mapIndex;
 						if(REFRACT && nsrc)
 							hitNormal = normal_of(nmask, nsrc == 2u ? c.step : m.step);
 						return true;

@@ -69,52 +69,7 @@ template <bool DEFER> static int run_lock_step(const DnbScene& S, const RayIn& r
 	return 0;
 }
 
-/* trace_ray with a start hint (RayState.startSlot): the right one where the ray's first cell holds a chunk (odd rays), a stale one --
- * some other tile's -- otherwise; must give exactly what trace_ray gives without a hint */
-static void run_hinted(const DnbScene& S, const RayIn& r, uint32_t i, RayOut& out)
-{
-	RayState st;
-	ray_state_reset(st);
-	st.lastVoxID = r.lastVoxID;
-	st.lastVoxRefract = r.lastVoxRefract;
-	const i3 cell = {(int)floorf(r.pos[0]), (int)floorf(r.pos[1]), (int)floorf(r.pos[2])};
-	uint32_t hinted = 0;
-	if((i & 1u) && in_map_bounds(S, cell))
-	{
-		const uint32_t idx = (uint32_t)cell.x + S.mapSize[0] * ((uint32_t)cell.y + S.mapSize[1] * (uint32_t)cell.z);
-		if(S.tileSlot[idx])
-		{
-			st.startSlot = S.tileSlot[idx];
-			st.startMapIndex = idx;
-			hinted = 1;
-		}
-	}
-	if(!hinted)
-	{
-		/* a stale hint: the first resident tile of the map, whatever the ray's first cell is */
-		for(uint32_t t = 0; t < S.numTiles; t++)
-			if(S.tileSlot[t])
-			{
-				st.startSlot = S.tileSlot[t];
-				st.startMapIndex = t;
-				break;
-			}
-	}
-	DnbCounters lc;
-	memset(&lc, 0, sizeof(lc));
-	f3 d = mk3(r.dir[0], r.dir[1], r.dir[2]), p = mk3(r.pos[0], r.pos[1], r.pos[2]), n = splat3(0.0f), colorAdd;
-	float colorMult;
-	const bool hit = trace_ray<false, false>(S, st, lc, d, rcp3(d), p, r.ignoreFirst != 0, n, colorAdd, colorMult);
-	fill(out, hit, st.tripped, st.lastVoxID, st.lastVoxRefract, st.hitMapIndex, st.hitLocalIndex, st.hitRecord, st.vox, p, colorAdd, colorMult);
-	out.deferred = hinted;
-	/* after a hit the state must carry the hint for a continuing segment: the hit tile and its slot */
-	if(hit && !(st.startMapIndex == st.hitMapIndex && st.startSlot == S.tileSlot[st.hitMapIndex]))
-		out.iterations = 0xDEAD;
-	if(!hit && st.startSlot != 0u)
-		out.iterations = 0xDEAD;
-}
-
-extern "C" int harness_run(const DnbScene* scene, const RayIn* rays, uint32_t count, RayOut* ref, RayOut* plain, RayOut* deferred, RayOut* hinted)
+extern "C" int harness_run(const DnbScene* scene, const RayIn* rays, uint32_t count, RayOut* ref, RayOut* plain, RayOut* deferred)
 {
 	const DnbScene S = *scene;
 	for(uint32_t i = 0; i < count; i++)
@@ -134,7 +89,6 @@ extern "C" int harness_run(const DnbScene* scene, const RayIn* rays, uint32_t co
 		}
 		if(run_lock_step<false>(S, r, plain[i]) || run_lock_step<true>(S, r, deferred[i]))
 			return -1;
-		run_hinted(S, r, i, hinted[i]);
 	}
 	return 0;
 }

@@ -1,10 +1,8 @@
-"""CPU check of the traversal variants against each other.  (1) The lock-step ray iteration the wavefront step kernel runs (csrc/ray_step.cuh): on scenes assembled in host memory it must
+"""CPU check of the lock-step ray iteration the wavefront step kernel runs (csrc/ray_step.cuh): on scenes assembled in host memory it must
 reproduce trace.cuh's trace_ray<false, false> -- the traversal of the other two lighting kernels, step_map + step_chunk of
 voxelShared.comp:328-475 -- bit for bit: hit flag, hit position, hit tile / voxel / record, transparency accumulators, the carried ray
 state; both with records fetched in the loop and with DEFERRED hits (all-opaque chunks end the ray on the voxel's bit; the record is
-fetched afterwards, as the serve kernel does).  (2) trace_ray with the start hint of RayState (the slot of the tile a lighting ray starts
-in, known to its caller): right hints, stale hints and no hint must give the same bits.
-Everything is compiled for the HOST with nvcc from the library's own headers; no GPU."""
+fetched afterwards, as the serve kernel does).  Everything is compiled for the HOST with nvcc from the library's own headers; no GPU."""
 import ctypes as C
 import os
 import shutil
@@ -44,7 +42,7 @@ def harness(tmp_path_factory):
     L = C.CDLL(out)
     L.harness_sizes.restype = C.c_size_t
     L.harness_run.restype = C.c_int
-    L.harness_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.harness_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     assert L.harness_sizes(0) == C.sizeof(Scene) and L.harness_sizes(1) == RAY_IN.itemsize and L.harness_sizes(2) == RAY_OUT.itemsize
     return L
 
@@ -110,12 +108,9 @@ def make_rays(rng, n, map_size, glass_ids):
 
 def compare(L, S, rays, what):
     n = len(rays)
-    ref, plain, deferred, hinted = np.zeros(n, RAY_OUT), np.zeros(n, RAY_OUT), np.zeros(n, RAY_OUT), np.zeros(n, RAY_OUT)
-    assert L.harness_run(C.byref(S), rays.ctypes.data, n, ref.ctypes.data, plain.ctypes.data, deferred.ctypes.data, hinted.ctypes.data) == 0
-    # trace_ray with a start hint (right ones and stale ones) == trace_ray without; the hint left behind after a hit is the hit tile's
-    assert not (hinted["iterations"] == 0xDEAD).any(), "%s: wrong start hint left in the ray state" % what
-    assert int(hinted["deferred"].sum()) > n // 50, "%s: too few rays exercised the hinted path" % what
-    for name, got in (("lock-step", plain), ("lock-step with deferred hits", deferred), ("trace_ray with start hints", hinted)):
+    ref, plain, deferred = np.zeros(n, RAY_OUT), np.zeros(n, RAY_OUT), np.zeros(n, RAY_OUT)
+    assert L.harness_run(C.byref(S), rays.ctypes.data, n, ref.ctypes.data, plain.ctypes.data, deferred.ctypes.data) == 0
+    for name, got in (("lock-step", plain), ("lock-step with deferred hits", deferred)):
         for f in RAY_OUT.names:
             if f in ("iterations", "deferred"):
                 continue
