@@ -104,6 +104,7 @@ bool device_create(VolumeImpl* v)
 	ok = ok && device_reserve(v->propagate, words ? words : 1, false, true, "propagate bitmap");
 	ok = ok && device_reserve(v->forced, words ? words : 1, false, true, "forced bitmap");
 	ok = ok && device_reserve(v->materials, DN_MAX_MATERIALS, false, true, "materials");
+	v->materialsOnDevice.clear();
 	ok = ok && device_reserve(v->slots, std::max<size_t>(vol->chunkCap, 64), false, true, "chunk slots");
 	ok = ok && device_reserve(v->records, std::max<size_t>(vol->voxelCap, 4096), false, true, "voxel records");
 	ok = ok && device_reserve(v->requests, 1024, false, false, "lighting requests");
@@ -193,13 +194,21 @@ void fill_scene(VolumeImpl* v, DnbScene* s)
 
 static void exact_opaque_bits(const DNvolume* vol, uint32_t bits[8]);
 
-/* uploads the material table (it travels with every draw and lighting call, as upstream: voxel.c:823-824) and keeps the slots'
+/* uploads the material table when it differs from the device's copy (upstream sends it with every draw and lighting call,
+ * voxel.c:823-824; a 4 KB host compare is cheaper than a copy node between two kernels of the frame) and keeps the slots'
  * DNB_BBOX_OPAQUE flags true: they were derived from the opacities of v->opaqueBits; when the application has changed an opacity
  * across 1.0 since, every slot's flag is re-derived on the device before anything traces */
 bool sync_materials(VolumeImpl* v, cudaStream_t s)
 {
 	DNvolume* vol = &v->pub;
-	bool ok = cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, sizeof(DNmaterial) * DN_MAX_MATERIALS, cudaMemcpyHostToDevice, s), "material upload");
+	const size_t tableBytes = sizeof(DNmaterial) * DN_MAX_MATERIALS;
+	if(v->materialsOnDevice.size() == tableBytes && memcmp(v->materialsOnDevice.data(), vol->materials, tableBytes) == 0)
+		return true; /* (the opaque flags were settled when this table was sent) */
+	bool ok = cuda_ok(cudaMemcpyAsync(v->materials.ptr, vol->materials, tableBytes, cudaMemcpyHostToDevice, s), "material upload");
+	if(ok)
+		v->materialsOnDevice.assign(reinterpret_cast<const unsigned char*>(vol->materials), reinterpret_cast<const unsigned char*>(vol->materials) + tableBytes);
+	else
+		v->materialsOnDevice.clear();
 	uint32_t bits[8];
 	exact_opaque_bits(vol, bits);
 	if(!v->opaqueBitsValid || memcmp(bits, v->opaqueBits, sizeof(bits)) != 0)

@@ -101,6 +101,7 @@ struct VolumeImpl
 	bool           forcedDirty = false;
 	uint32_t       opaqueBits[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* materials with opacity == 1.0 in the table the slots' DNB_BBOX_OPAQUE flags were derived from */
 	bool           opaqueBitsValid = false;
+	std::vector<unsigned char> materialsOnDevice;            /* the table as last uploaded: an unchanged table is not sent again */
 
 	/* ---- the lighting-request list of the last reading sync.  Its length stays on the device (scalars[0], read there by the lighting
 	 * and commit kernels: layout.h DnbWork); the host knows an upper bound at once and the exact number when it asks (request_count) ---- */

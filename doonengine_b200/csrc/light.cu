@@ -333,8 +333,16 @@ DNB_FN void light_voxel(const DnbScene& S, LightCtx& cx, uint4 rec, const DnbMat
 	pack_lit_words(rec, spec.c, diff.c, w1, w2, w3);
 }
 
-template <bool COUNT>
+/* SKIP_SPECULAR: leave the voxels that trace specular rays to somebody else (light_spread.cuh) */
+template <bool COUNT, bool SKIP_SPECULAR = false>
 DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ requests, uint32_t r, uint32_t warp, uint32_t lane, const DnbStagingTargets& T, DnbSlot* s_slot);
+
+/* LI:239-242: does this voxel trace its 15 specular rays? */
+DNB_FN bool traces_specular(const DnbMaterial& material, f3 rayPos, f3 normal)
+{
+	const f3 viewDir = rayPos - ld3(c_light.camPos);
+	return material.specular > 0.0f && dot3(viewDir, normal) < 0.0f && material.reflectType <= 1u;
+}
 
 /* grid-stride over this launch's CTAs of 4 requests: the grid is sized from what the host knows (an upper bound and the last count it
  * saw), the real count is read on the device */
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(128) dn_light_kernel(DnbScene S, const uint32_
 	}
 }
 
-template <bool COUNT>
+template <bool COUNT, bool SKIP_SPECULAR>
 DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ requests, uint32_t r, uint32_t warp, uint32_t lane, const DnbStagingTargets& T, DnbSlot* s_slot)
 {
 	const uint32_t request = __ldg(requests + r);
@@ -403,6 +411,8 @@ DNB_FN void light_request(const DnbScene& S, const uint32_t* __restrict__ reques
 	/* LI:231-232 */
 	f3 rayPos = (tof3(chunkPos) * 0.125f + tof3(mapPos)) + 0.0625f;
 	rayPos = rayPos + normal * (0.0625f - DNB_EPSILON);
+	if(SKIP_SPECULAR && traces_specular(material, rayPos, normal))
+		return;
 
 	uint32_t w1, w2, w3;
 	light_voxel<COUNT>(S, cx, rec, material, rayPos, indirectSamples, w1, w2, w3);

@@ -1,5 +1,6 @@
-/* light_spread.cuh (included at the end of light.cu) -- the lighting update for SMALL dispatches: one warp per VOXEL, its rays spread
- * over the lanes ("spread" lighting kernel).
+/* light_spread.cuh (included at the end of light.cu) -- the lighting update for SMALL dispatches: a voxel that traces specular rays gets
+ * a whole warp, its rays spread over the lanes ("spread" lighting kernel); the other voxels (two short rays each) are lit one per lane
+ * by their request's warp, exactly as in the warp-per-request kernel.
  *
  * A shader invocation traces up to 15 specular rays of up to specularBounceLimit segments, then per diffuse sample a path of up to
  * diffuseBounceLimit segments and a shadow ray -- one after the other (LI:244-261).  With one thread per voxel that is a serial chain
@@ -24,17 +25,32 @@
 #define SPREAD_WARPS 4
 
 template <int DUMMY>
-__global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W, DnbStagingTargets T)
+__global__ void __launch_bounds__(SPREAD_WARPS * 32, 5) dn_light_spread_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W, DnbStagingTargets T)
 {
 	__shared__ float s_add[SPREAD_WARPS][32][DNB_MAX_ADDENDS][3];
 	__shared__ uint32_t s_num[SPREAD_WARPS][32];
+	__shared__ DnbSlot s_slot[SPREAD_WARPS];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t numRequests = work_requests(W);
-	const uint32_t totalItems = work_ctas(W, numRequests) * 128u; /* a work item = one lane of a request = one voxel */
+	/* work items, one per warp: first every request of this launch (its voxels WITHOUT specular rays, one per lane, the plain way:
+	 * two short rays each -- and the empty rows of the request), then every voxel of every request (its rays spread over the lanes;
+	 * taken only if it traces specular rays).  Both kinds decide with the same predicate, so every staged row has exactly one writer. */
+	const uint32_t requestItems = work_ctas(W, numRequests) * 4u;
+	const uint32_t totalItems = requestItems * 33u;
 	const uint32_t n = c_light.numDiffuseSamples;
 
-	for(uint32_t j = blockIdx.x * SPREAD_WARPS + warp; j < totalItems; j += gridDim.x * SPREAD_WARPS)
+	for(uint32_t item = blockIdx.x * SPREAD_WARPS + warp; item < totalItems; item += gridDim.x * SPREAD_WARPS)
 	{
+		if(item < requestItems)
+		{
+			const uint32_t r = (W.firstCta + (item >> 2) * W.ctaStride) * 4u + (item & 3u);
+			if(r < numRequests)
+				light_request<false, true>(S, requests, r, warp, lane, T, s_slot);
+			__syncwarp();
+			continue;
+		}
+		const uint32_t j = item - requestItems; /* voxel j & 31 of request (j >> 5) */
+
 		/* ---- set-up, LI:207-232: every lane computes the same (the loads are broadcasts) ---- */
 		const uint32_t r = (W.firstCta + (j >> 7) * W.ctaStride) * 4u + ((j >> 5) & 3u);
 		if(r >= numRequests)
@@ -47,11 +63,7 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbS
 		const uint32_t voxNum = (j & 31u) + (request & 15u) * 32u;
 		const int local = slotId == 0xFFFFFFFFu ? -1 : flat_nth_voxel(slot, voxNum);
 		if(local < 0)
-		{
-			if(lane == 0)
-				stage_words(T, at, 0, 0, 0);
-			continue;
-		}
+			continue; /* (the request's own work item has staged the empty row) */
 		const uint4 rec = __ldg(S.records + (__ldg(&slot->voxelBase) + voxNum));
 		const f3 normal = vox_normal(rec);
 		const f3 albedo = vox_albedo(rec);
@@ -62,6 +74,8 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbS
 		const i3 mapPos = {__ldg(&slot->pos[0]), __ldg(&slot->pos[1]), __ldg(&slot->pos[2])};
 		f3 rayPos = (tof3(chunkPos) * 0.125f + tof3(mapPos)) + 0.0625f;
 		rayPos = rayPos + normal * (0.0625f - DNB_EPSILON);
+		if(!traces_specular(material, rayPos, normal))
+			continue; /* lit by its request's work item */
 
 		LightCtx cx;
 		ray_state_reset(cx.st);
@@ -70,7 +84,6 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbS
 		cx.sourceVisible = (__ldg(S.visible + (mapIndex >> 5)) >> (mapIndex & 31u)) & 1u;
 
 		const f3 viewDir = rayPos - ld3(c_light.camPos);
-		const bool specular = material.specular > 0.0f && dot3(viewDir, normal) < 0.0f && material.reflectType <= 1u;
 		const bool diffuse = material.specular < 1.0f;
 
 		/* ---- this lane's ray ---- */
@@ -79,7 +92,6 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbS
 		acc.numTiles = 0;
 		if(lane < 15u)
 		{
-			if(specular)
 			{
 				const f3 reflected = reflect3(normalize3(viewDir), normal);
 				const f3 specDir = normalize3(reflected * (float)material.shininess + ld3(c_spherePoints[lane])) + DNB_EPSILON;
@@ -133,7 +145,6 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32) dn_light_spread_kernel(DnbS
 		if(lane == 0)
 		{
 			f3 specLight = splat3(0.0f), diffuseLight = splat3(0.0f);
-			if(specular)
 			{
 				for(uint32_t i = 0; i < 15u; i++)
 					for(uint32_t k = 0; k < s_num[warp][i]; k++)
@@ -171,8 +182,8 @@ extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint
 {
 	if(gridCtas == 0)
 		return cudaSuccess;
-	/* gridCtas counts 4-request CTAs = 128 voxels = 128 warps of this kernel; the kernel strides, so the grid is only capped */
-	const unsigned long long want = (unsigned long long)gridCtas * (128u / SPREAD_WARPS);
+	/* gridCtas counts 4-request CTAs = 4 request items + 128 voxel items, a warp each; the kernel strides, so the grid is only capped */
+	const unsigned long long want = (unsigned long long)gridCtas * (132u / SPREAD_WARPS);
 	const uint32_t grid = (uint32_t)(want < 148ull * 64ull ? want : 148ull * 64ull);
 	{ DNB_LAUNCHED(1); dn_light_spread_kernel<0><<<grid, SPREAD_WARPS * 32, 0, stream>>>(*scene, requests, *work, *targets); }
 	return cudaGetLastError();
