@@ -1392,7 +1392,7 @@ extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint
  * candidate only up to SPREAD_MAX_REQUESTS requests: it spends a warp per voxel).  Every dispatch is bracketed by two events (no
  * synchronisation: they are read one or two dispatches later, once they have completed anyway); the first dispatches rotate through
  * the candidates until each has two timings (the very first one, the jitter-free first sample, is not representative and is not
- * used), then the fastest one runs, with 5 % hysteresis, and the others are re-timed in turn every 64th dispatch in case the camera
+ * used), then the fastest one runs, with 5 % hysteresis, and the others are re-timed in turn every 64th dispatch (every 1024th if they were more than twice as slow) in case the camera
  * or the map has changed.  The wavefront pair is not a candidate: measured on B200 after round 2's dropped-item fix it is slower
  * than the persistent kernel on every configuration (profiles/r2_light.md); it stays selectable explicitly. */
 static const size_t SPREAD_MAX_REQUESTS = 8192;
@@ -1453,7 +1453,15 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool spreadEligibl
 			for(int c = 0; c < numCand; c++)
 				if(cand[c] == k)
 					at = c;
-			k = cand[(at + 1 + (int)((n >> 6) % (uint64_t)(numCand - 1))) % numCand];
+			/* a candidate that was more than twice as slow is looked at 16 times less often: on the demo map one re-timed
+			 * warp-per-request dispatch costs as much as eight dispatches of the kernel that runs */
+			const uint64_t tick = n >> 6;
+			const bool rare = (tick & 15u) == 15u;
+			const int other = cand[(at + 1 + (int)((rare ? tick >> 4 : tick) % (uint64_t)(numCand - 1))) % numCand];
+			if(rare || t.nsPerCta[other] < 2.0 * t.nsPerCta[k])
+				k = other;
+			else
+				t.lastKernel = k;
 		}
 		else
 			t.lastKernel = k;
