@@ -211,6 +211,16 @@ def cpu_baseline(scene, tiles, chunks, camera, res, budget_s=20.0, max_frames=8)
     return out
 
 
+def lit_by_requests(e):
+    """voxels a lighting dispatch of the reference engine has just processed: per request (tile << 4 | group) the surface voxels of that
+    32-voxel group (voxelLighting.comp:212-217), counted from the chunk buffer's bit masks (the reference's shaders keep no counters)"""
+    req = e.requests()
+    if len(req) == 0:
+        return 0
+    n = np.bitwise_count(e.chunk_view()["bitMask"][req >> 4]).sum(axis=1).astype(np.int64)
+    return int(np.clip(n - 32 * (req & 15).astype(np.int64), 0, 32).sum())
+
+
 def run_reference(args, scene, tiles, res, desc):
     """--impl reference: the reference's own host code (voxel.c compiled in place, oracle/_ref) driving the CPU
     restatement of its shaders on all host cores.  Falls back to the restated host (oracle port) when the
@@ -228,7 +238,11 @@ def run_reference(args, scene, tiles, res, desc):
         return
     chunks, camera = make_chunks(scene, tiles) if scene != "demo" else ([], {})
     kind = "reference" if O.have_ref() else "port"
-    cls = O.RefEngine if kind == "reference" else O.OracleEngine
+    # the reference's host code dispatching the reference's OWN shaders (their GLSL text compiled as C++ where it lies, oracle/glsl/),
+    # when that library was built; else the reference's host code dispatching the restatement of the shaders; else the restated host
+    shaders = "reference GLSL compiled as C++ (oracle/_ref/libglsl_ref.so)" if kind == "reference" and O.have_glsl() else "CPU restatement (oracle/shader_cpu.c)"
+    import functools
+    cls = (functools.partial(O.RefEngine, glsl=True) if O.have_glsl() else O.RefEngine) if kind == "reference" else O.OracleEngine
     # the reference sizes its voxel pool as 512*minChunks/2 (voxel.c:190): twice the chunk count keeps everything resident
     e = build_engine(cls, scene, tiles, chunks, camera, min_chunks=2 * len(chunks) + 32)
     e.sync(1, 1)
@@ -244,13 +258,14 @@ def run_reference(args, scene, tiles, res, desc):
         e.update_lighting(1, 1000, frame_time(k))
         t2 = time.perf_counter()
         if k >= args.warmup:
-            lit += e.counters()["light"]["voxelsLit"]
+            lit += lit_by_requests(e) if kind == "reference" else e.counters()["light"]["voxelsLit"]
             t_light += t2 - t1
             t_frame += t2 - t0
             reqs += len(e.requests())
     value = lit / t_light if t_light > 0 else 0.0
     K = max(args.steps, 1)
-    sample = "each step = %dx%d draw + sync + 1 lighting dispatch over the chunks that draw made visible (%d requests, %d voxels lit per step), %d OpenMP threads" % (w, h, reqs // K, lit // K, cores)
+    sample = "each step = %dx%d draw + sync + 1 lighting dispatch over the chunks that draw made visible (%d requests, %d voxels lit per step), %d OpenMP threads; host: %s; shaders: %s" % (
+        w, h, reqs // K, lit // K, cores, "reference voxel.c (oracle/_ref/libdoon_ref.so)" if kind == "reference" else "restated (oracle/host_cpu.c)", shaders)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_frame / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
