@@ -131,6 +131,7 @@ typedef struct DnbPeerTable
 typedef struct DnbFlatTuning
 {
 	int budget, endLanes, patience;
+	int endMax; /* 1: finished rays are also served as soon as they are the most populated state of the warp */
 } DnbFlatTuning;
 
 /* the staging arrays one lighting launch stores into: its own, or every replica's */

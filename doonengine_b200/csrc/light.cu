@@ -520,7 +520,7 @@ __global__ void dn_merge_visible_peers_kernel(DnbPeerTable T, uint32_t* __restri
 #include "light_wave.cuh"
 #include "light_spread.cuh"
 
-static DnbFlatTuning g_flatTuning = {0, 0, 0};
+static DnbFlatTuning g_flatTuning = {0, 0, 0, 0};
 
 /* scheduling knobs of the persistent kernel (experiments; results do not depend on them) */
 extern "C" void DN_b200_set_flat_tuning(int budget, int endLanes, int patience)
@@ -569,6 +569,13 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 			tuning.endLanes = knob("DN_B200_FLAT_END", 28);
 			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 16);
 		}
+		static int endMax = -1;
+		if(endMax < 0)
+		{
+			const char* e = getenv("DN_B200_FLAT_ENDMAX");
+			endMax = e ? atoi(e) != 0 : 0;
+		}
+		tuning.endMax = endMax;
 		{ DNB_LAUNCHED(1); dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, *work, flatCounter, *targets, tuning); }
 	}
 	else

@@ -31,7 +31,7 @@
  * reset per voxel, as one invocation lights one voxel.  Lighting never refracts (LI:209), so the chunk-level DDA shares
  * the tile-level DDA's step and delta vectors.
  */
-enum : uint32_t { ST_FETCH = 0, ST_TILE = 1, ST_VOX = 2, ST_END = 3, ST_DONE = 4 };
+enum : uint32_t { ST_FETCH = 0, ST_TILE = 1, ST_VOX = 2, ST_END = 3, ST_DONE = 4, ST_ENTER = 5 };
 enum : uint32_t { RAY_SPEC = 0, RAY_DIFFUSE = 1, RAY_SHADOW = 2 };
 
 struct FlatLane
@@ -90,6 +90,41 @@ DNB_FN void flat_start_ray(FlatLane& L, uint32_t& state)
 	state = ST_TILE;
 }
 
+/* chunk entry, SH:443-445 and step_chunk's prologue: the dearest operation of a ray segment (~95 instructions, two dependent loads).
+ * Inside the tile step it ran with the ~4 lanes that happened to find a chunk in the same iteration; as a phase of its own it runs
+ * when it is the most populated state of the warp. */
+DNB_FN void flat_enter_chunk(const DnbScene& S, FlatLane& L, uint32_t& state)
+{
+	Dda& m = L.m;
+	/* resident chunk: SH:443-445, then step_chunk's prologue */
+	L.mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
+	L.slot = S.slots + (__ldg(S.tileSlot + L.mapIndex) - 1u);
+	L.tile = tof3(m.pos);
+	const f3 entry = L.pos + L.dir * (L.tLast - DNB_EPSILON);
+	f3 cpos = (entry - L.tile) * 8.0f;
+	cpos = min3v(max3v(cpos, splat3(DNB_EPSILON)), splat3(8.0f - DNB_EPSILON));
+	L.cpos = cpos;
+	/* init_dda(rayDir, invRayDir, cpos, c): delta and step equal the tile level's */
+	const f3 cell = floor3(cpos);
+	L.cp = toi3(cell);
+	const f3 sg = mk3(sgn(L.dir.x), sgn(L.dir.y), sgn(L.dir.z));
+	const f3 t = sg * (cell - cpos) + sg * 0.5f;
+	L.cside = (t + 0.5f) * m.delta;
+	L.ctLast = 0.0f;
+	L.cguard = 0;
+	/* both loads that depend on the slot index leave together (the entry cell's mask word and the bounding-box word, whose top
+	 * bit says whether every material of the chunk is opaque: trace.cuh) */
+	L.wordIdx = ((uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z)) >> 5;
+	L.word = __ldg(L.slot->mask + L.wordIdx);
+	const uint32_t bbox = __ldg(&L.slot->bbox);
+	L.chunkOpaque = (bbox & DNB_BBOX_OPAQUE) != 0u;
+	L.cbias = 0;
+	L.coffp = 0;
+	if(L.st.lastVoxID == 255u)
+		L.coffp = cull_offsets(bbox, m.step, L.cp, L.cbias);
+	state = ST_VOX;
+}
+
 /* one iteration of trace_ray's phase-A loop */
 DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 {
@@ -130,33 +165,8 @@ DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 	const uint32_t bit = (uint32_t)(m.pos.x & 3) | ((uint32_t)(m.pos.y & 3) << 2) | ((uint32_t)(m.pos.z & 3) << 4);
 	if((L.occWord >> bit) & 1ull)
 	{
-		/* resident chunk: SH:443-445, then step_chunk's prologue */
-		L.mapIndex = (uint32_t)m.pos.x + S.mapSize[0] * ((uint32_t)m.pos.y + S.mapSize[1] * (uint32_t)m.pos.z);
-		L.slot = S.slots + (__ldg(S.tileSlot + L.mapIndex) - 1u);
-		L.tile = tof3(m.pos);
-		const f3 entry = L.pos + L.dir * (L.tLast - DNB_EPSILON);
-		f3 cpos = (entry - L.tile) * 8.0f;
-		cpos = min3v(max3v(cpos, splat3(DNB_EPSILON)), splat3(8.0f - DNB_EPSILON));
-		L.cpos = cpos;
-		/* init_dda(rayDir, invRayDir, cpos, c): delta and step equal the tile level's */
-		const f3 cell = floor3(cpos);
-		L.cp = toi3(cell);
-		const f3 sg = mk3(sgn(L.dir.x), sgn(L.dir.y), sgn(L.dir.z));
-		const f3 t = sg * (cell - cpos) + sg * 0.5f;
-		L.cside = (t + 0.5f) * m.delta;
-		L.ctLast = 0.0f;
-		L.cguard = 0;
-		/* both loads that depend on the slot index leave together (the entry cell's mask word and the bounding-box word, whose top
-		 * bit says whether every material of the chunk is opaque: trace.cuh) */
-		L.wordIdx = ((uint32_t)L.cp.x + 8u * ((uint32_t)L.cp.y + 8u * (uint32_t)L.cp.z)) >> 5;
-		L.word = __ldg(L.slot->mask + L.wordIdx);
-		const uint32_t bbox = __ldg(&L.slot->bbox);
-		L.chunkOpaque = (bbox & DNB_BBOX_OPAQUE) != 0u;
-		L.cbias = 0;
-		L.coffp = 0;
-		if(L.st.lastVoxID == 255u)
-			L.coffp = cull_offsets(bbox, m.step, L.cp, L.cbias);
-		state = ST_VOX;
+		/* resident chunk: entered as a phase of its own (flat_enter_chunk), by all the lanes that have found one */
+		state = ST_ENTER;
 		return;
 	}
 	iterate_dda(m, L.tLast);
@@ -558,11 +568,12 @@ __global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_fla
 		const uint32_t mT = __ballot_sync(0xFFFFFFFFu, state == ST_TILE);
 		const uint32_t mV = __ballot_sync(0xFFFFFFFFu, state == ST_VOX);
 		const uint32_t mE = __ballot_sync(0xFFFFFFFFu, state == ST_END || state == ST_FETCH);
-		const int nT = __popc(mT), nV = __popc(mV), nE = __popc(mE);
-		if(nT + nV + nE == 0)
+		const uint32_t mN = __ballot_sync(0xFFFFFFFFu, state == ST_ENTER);
+		const int nT = __popc(mT), nV = __popc(mV), nE = __popc(mE), nN = __popc(mN);
+		if(nT + nV + nE + nN == 0)
 			break;
 
-		if(nE >= K.endLanes || nT + nV == 0 || (nE > 0 && waited >= K.patience))
+		if(nE >= K.endLanes || nT + nV + nN == 0 || (nE > 0 && (waited >= K.patience || (K.endMax && nE >= nT && nE >= nV && nE >= nN))))
 		{
 			/* shade finished rays and pick the next ones; hand free lanes new voxels; then start all new rays together */
 			waited = 0;
@@ -601,6 +612,12 @@ __global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_fla
 			}
 			if(start)
 				flat_start_ray(L, state);
+		}
+		else if(nN > 0 && nN >= nT && nN >= nV)
+		{
+			if(state == ST_ENTER)
+				flat_enter_chunk(S, L, state);
+			waited++;
 		}
 		else if(nT >= nV)
 		{

@@ -34,7 +34,13 @@ view, proj = e.view_projection(h / w)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 names = sys.argv[3].split(",") if len(sys.argv) > 3 else ["warp", "flat", "wave"]
-variants = [(n, (24, 28, 16) if n == "flat" else None) for n in names]
+def env_knob(name, dflt):
+    return int(os.environ.get(name, dflt))
+
+
+# the persistent kernel's knobs: from the environment when set there (DN_B200_FLAT_ENDMAX is read by the library itself)
+flat_knobs = (env_knob("DN_B200_FLAT_BUDGET", 24), env_knob("DN_B200_FLAT_END", 28), env_knob("DN_B200_FLAT_PATIENCE", 16))
+variants = [(n, flat_knobs if n == "flat" else None) for n in names]
 out = []
 k = 0
 for name, knobs in variants:
