@@ -462,7 +462,10 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
         if timed:
             marks[4].record(stream)
         if read_back:
-            L.DN_b200_wait_framebuffer_read(fbs[(k - 1) % 3])  # frame k-1's pixels are on the host
+            # frame k-2's pixels are on the host: the oldest of the three buffers, the one frame k+1 draws into next.  (Waiting for frame
+            # k-1 here kept the host at most one frame ahead of the device; on the edit stream, where a frame's upload depends on 2 ms of
+            # host packing, that left the GPU idle for a quarter of every frame.)
+            L.DN_b200_wait_framebuffer_read(fbs[(k - 2) % 3])
         t7 = time.perf_counter()
         if timed:
             marks[5].record(stream)
@@ -638,7 +641,7 @@ def measure_config(args, env, config, steps, warmup, want_cpu):
                          "wall_per_step_incl_flush": 1000.0 * wall / K},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8192 + 2416, "d2h_bytes_per_step": fb_bytes + 4, "ms_per_step": frame2_ms,
                     "l2_flush_ms_per_step": flush2_ms, "ms_per_step_without_l2_flush": frame2_ms - flush2_ms,
-                    "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps frame k+1; N > 1: every replica copies the rows it drew into one shared pinned mapping); timed as ONE region from the first draw to the last copy landing, L2 flushes and host gaps between steps included"},
+                    "note": "through DN_draw / DN_sync_gpu / DN_update_lighting with the framebuffer copied to pinned host memory every step (3 framebuffers in rotation: the copy of frame k overlaps the next frames, the host takes delivery of frame k-2 during frame k; N > 1: every replica copies the rows it drew into one shared pinned mapping); timed as ONE region from the first draw to the last copy landing, L2 flushes and host gaps between steps included"},
             "gpu_launches": launches,
             "host_ms_per_step_e2e": {k_: (1000.0 * v_ / max(host_s["steps"], 1)) for k_, v_ in host_s.items() if k_ != "steps"},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

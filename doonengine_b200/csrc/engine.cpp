@@ -854,7 +854,8 @@ static void sync_read(VolumeImpl* v, uint32_t split)
 	 * into a pinned host word; nobody waits for it here: the host sizes everything from the bound it knows, and reads the exact
 	 * number only when somebody asks (request_count) */
 	Context& cx = ctx();
-	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, v->pinnedScalars, s), "compaction count");
+	v->syncSerial++; /* a ring of four host words: the lighting-kernel tuner reads the count of the dispatch it timed a frame or two later */
+	cuda_ok(dnb_launch_compact_count(&scene, forced, split, vol->frameNum, v->blockCounts.ptr, v->blockOffsets.ptr, v->scalars.ptr, v->pinnedScalars + (v->syncSerial & 3u), s), "compaction count");
 	cuda_ok(cudaEventRecord(cx.evCountDone, s), "event record");
 	cuda_ok(dnb_launch_compact_write(&scene, forced, split, vol->frameNum, v->blockOffsets.ptr, v->requests.ptr, s), "compaction write");
 	v->requestBound = v->residentGroups;
@@ -880,7 +881,7 @@ size_t request_count(VolumeImpl* v, bool wait)
 		cudaError_t q = wait ? cudaEventSynchronize(cx.evCountDone) : cudaEventQuery(cx.evCountDone);
 		if(q == cudaSuccess)
 		{
-			v->requestsValid = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars);
+			v->requestsValid = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars + (v->syncSerial & 3u));
 			v->lastExactCount = v->requestsValid;
 			v->pub.numLightingRequests = v->requestsValid;
 			v->countPending = false;
@@ -1396,7 +1397,7 @@ extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint
  * or the map has changed.  The wavefront pair is not a candidate: measured on B200 after round 2's dropped-item fix it is slower
  * than the persistent kernel on every configuration (profiles/r2_light.md); it stays selectable explicitly. */
 static const size_t SPREAD_MAX_REQUESTS = 8192;
-static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool spreadEligible, cudaStream_t s, int* slotOut)
+static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool ctasExact, uint32_t firstCta, uint32_t ctaStride, bool spreadEligible, cudaStream_t s, int* slotOut)
 {
 	VolumeImpl::LightTuner& t = v->tuner;
 	*slotOut = -1;
@@ -1410,10 +1411,25 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool spreadEligibl
 		if(t.slotKernel[slot] < 0 || cudaEventQuery(t.end[slot]) != cudaSuccess)
 			continue;
 		float ms = 0.0f;
-		if(cudaEventElapsedTime(&ms, t.begin[slot], t.end[slot]) == cudaSuccess && t.slotCtas[slot] > 0)
+		/* the CTAs the dispatch really had: the host sized it from a count that lags a frame behind (and while the visible set is
+		 * still growing, by a lot: a kernel timed then looked a hundred times slower per CTA than it is); the device has published
+		 * the real count in the meantime, unless four more syncs have gone by */
+		uint32_t ctas = t.slotCtas[slot];
+		if(!t.slotExact[slot])
+		{
+			if(v->syncSerial - t.slotSerial[slot] >= 4u)
+				ctas = 0;
+			else
+			{
+				const uint32_t exact = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars + (t.slotSerial[slot] & 3u));
+				const uint32_t total = (exact + 3u) / 4u;
+				ctas = total > t.slotFirstCta[slot] ? (total - t.slotFirstCta[slot] + t.slotStride[slot] - 1u) / t.slotStride[slot] : 0u;
+			}
+		}
+		if(cudaEventElapsedTime(&ms, t.begin[slot], t.end[slot]) == cudaSuccess && ctas > 0)
 		{
 			const int k = t.slotKernel[slot];
-			const double ns = 1e6 * (double)ms / (double)t.slotCtas[slot];
+			const double ns = 1e6 * (double)ms / (double)ctas;
 			/* running minimum that may rise by at most 3 % per sample: interference (another process on the box, a clock dip)
 			 * only ever makes a dispatch slower, so one slow sample must not dethrone the faster kernel */
 			t.nsPerCta[k] = t.samples[k] == 0 ? ns : std::min(ns, 1.03 * t.nsPerCta[k]);
@@ -1476,6 +1492,10 @@ static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool spreadEligibl
 					break;
 				t.slotKernel[slot] = k;
 				t.slotCtas[slot] = numCtas;
+				t.slotExact[slot] = ctasExact;
+				t.slotSerial[slot] = v->syncSerial;
+				t.slotFirstCta[slot] = firstCta;
+				t.slotStride[slot] = ctaStride ? ctaStride : 1u;
 				cudaEventRecord(t.begin[slot], s);
 				*slotOut = slot;
 				break;
@@ -1630,7 +1650,7 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
 	int timingSlot = -1;
 	const bool spreadEligible = expect <= SPREAD_MAX_REQUESTS && dnb_light_spread_usable(lp.numDiffuseSamples, lp.specularBounceLimit);
-	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, spreadEligible, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
+	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, needExact, firstCta, ctaStride, spreadEligible, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
 	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself, and so does the persistent kernel
 	 * (4-byte stores as its lanes finish, but overlapped with its ray tracing: measured faster at 8 replicas than a push afterwards,
 	 * 302 vs 349 ns per 4 requests on config 3); the wavefront kernels stage locally and their rows are pushed to the peers

@@ -96,7 +96,8 @@ struct VolumeImpl
 	size_t         pinnedBlobCaps[2] = {0, 0};
 	cudaEvent_t    blobDone[2] = {nullptr, nullptr}; /* the batch that last used the pair has been scattered */
 	unsigned       blobTurn = 0;
-	uint32_t*      pinnedScalars = nullptr;    /* read-back of the request count */
+	uint32_t*      pinnedScalars = nullptr;    /* read-back of the request count: a ring of four words, [syncSerial & 3] */
+	uint64_t       syncSerial = 0;             /* reading syncs so far */
 	DnbCounters*   counters = nullptr;         /* device, NULL when instrumentation is off */
 	bool           forcedDirty = false;
 	uint32_t       opaqueBits[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* materials with opacity == 1.0 in the table the slots' DNB_BBOX_OPAQUE flags were derived from */
@@ -125,7 +126,10 @@ struct VolumeImpl
 	{
 		cudaEvent_t begin[2] = {nullptr, nullptr}, end[2] = {nullptr, nullptr}; /* two timing slots in rotation */
 		int      slotKernel[2] = {-1, -1};   /* kernel timed in each slot, -1 = slot free */
-		uint32_t slotCtas[2] = {0, 0};
+		uint32_t slotCtas[2] = {0, 0};        /* CTAs of the timed dispatch as the host estimated them ... */
+		bool     slotExact[2] = {false, false}; /* ... which is exact (host-driven sharding), or replaced at harvest by the count the device published: */
+		uint64_t slotSerial[2] = {0, 0};      /* the reading sync whose list the dispatch worked on (pinnedScalars ring) */
+		uint32_t slotFirstCta[2] = {0, 0}, slotStride[2] = {1, 1};
 		double   nsPerCta[4] = {0.0, 0.0, 0.0, 0.0}; /* running estimate per kernel: 0 warp per request, 1 persistent, 2 wavefront, 3 spread */
 		uint32_t samples[4] = {0, 0, 0, 0};
 		uint64_t dispatches = 0;

@@ -566,8 +566,8 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 		{
 			auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
 			tuning.budget = knob("DN_B200_FLAT_BUDGET", 24);
-			tuning.endLanes = knob("DN_B200_FLAT_END", 28);
-			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 16);
+			tuning.endLanes = knob("DN_B200_FLAT_END", 20);
+			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 32);
 		}
 		static int endMax = -1;
 		if(endMax < 0)

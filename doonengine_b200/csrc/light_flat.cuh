@@ -31,6 +31,11 @@
  * reset per voxel, as one invocation lights one voxel.  Lighting never refracts (LI:209), so the chunk-level DDA shares
  * the tile-level DDA's step and delta vectors.
  */
+/* opaque hits leave their record to the END phase (flat_hit_record); 0 = fetch it inside the voxel step, as before (A/B builds) */
+#ifndef FLAT_DEFER_RECORD
+#define FLAT_DEFER_RECORD 1
+#endif
+
 enum : uint32_t { ST_FETCH = 0, ST_TILE = 1, ST_VOX = 2, ST_END = 3, ST_DONE = 4, ST_ENTER = 5 };
 enum : uint32_t { RAY_SPEC = 0, RAY_DIFFUSE = 1, RAY_SHADOW = 2 };
 
@@ -200,12 +205,25 @@ DNB_FN void flat_vox_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 
 	if(((L.word >> (local & 31u)) & 1u) && !L.ignoreFirst)
 	{
+		if(FLAT_DEFER_RECORD && L.chunkOpaque)
+		{
+			/* every material of this chunk is opaque: the set bit IS the hit (SH:351).  The record -- prefix count, record base, record:
+			 * a chain of dependent loads that ran here with ~2 lanes -- is fetched by the END phase (flat_hit_record), and only by the
+			 * ray kinds that look at it (a shadow ray does not) */
+			const f3 cpos = L.cpos + L.dir * (L.ctLast + DNB_EPSILON);
+			L.pos = L.tile + cpos * 0.125f;
+			L.st.hitMapIndex = L.mapIndex;
+			L.st.hitLocalIndex = local;
+			L.hit = true;
+			state = ST_END;
+			return;
+		}
 		const uint32_t rel = (uint32_t)__ldg(L.slot->prefix + L.wordIdx) + __popc(L.word & ((1u << (local & 31u)) - 1u));
 		const uint4 rec = __ldg(S.records + (__ldg(&L.slot->voxelBase) + rel));
 		L.st.vox = rec;
 		DnbMaterial material;
 		material.opacity = 1.0f;
-		if(!L.chunkOpaque)
+		if(FLAT_DEFER_RECORD || !L.chunkOpaque)
 			material = load_material(S, rec.x >> 24);
 		const uint32_t thisVoxID = (rec.y & 0xFFFFFF00u) | (rec.x >> 24);
 
@@ -375,6 +393,19 @@ DNB_FN bool flat_begin_diffuse(const DnbScene& S, const DnbStagingTargets& T, Fl
 }
 
 /* a ray segment has ended (L.hit says how): specular_ray LI:96-145, diffuse_ray LI:174-202, shadow_ray LI:77-79 after their trace */
+/* the record of the voxel the segment has hit; hits in all-opaque chunks left it unfetched (flat_vox_step) */
+DNB_FN uint4 flat_hit_record(const DnbScene& S, FlatLane& L)
+{
+	if(FLAT_DEFER_RECORD && L.chunkOpaque)
+	{
+		const uint32_t local = L.st.hitLocalIndex;
+		const uint32_t rel = (uint32_t)__ldg(L.slot->prefix + L.wordIdx) + __popc(L.word & ((1u << (local & 31u)) - 1u));
+		L.st.hitRecord = rel;
+		L.st.vox = __ldg(S.records + (__ldg(&L.slot->voxelBase) + rel));
+	}
+	return L.st.vox;
+}
+
 DNB_FN bool flat_ray_ended(const DnbScene& S, const DnbStagingTargets& T, FlatLane& L, uint32_t& state)
 {
 	const f3 sunDir = ld3(c_light.sunDir);
@@ -393,7 +424,7 @@ DNB_FN bool flat_ray_ended(const DnbScene& S, const DnbStagingTargets& T, FlatLa
 			const f3 dist = abs3(floor3(L.pos * 8.0f) - floor3(L.pa * 8.0f));
 			if(!(dot3(dist, dist) <= 1.0f))
 			{
-				const uint4 rec = L.st.vox;
+				const uint4 rec = flat_hit_record(S, L);
 				const DnbMaterial hm = load_material(S, vox_material(rec));
 				const f3 hitAlbedo = vox_albedo(rec);
 				const f3 hitDiffuse = vox_diffuse(rec) * (1.0f - hm.specular);
@@ -437,10 +468,10 @@ DNB_FN bool flat_ray_ended(const DnbScene& S, const DnbStagingTargets& T, FlatLa
 	{
 		if(L.hit)
 		{
-			const uint4 rec = L.st.vox;
 			const f3 dist = abs3(floor3(L.origin * 8.0f) - floor3(L.pos * 8.0f));
 			if(!(dot3(dist, dist) < 1.0f))
 			{
+				const uint4 rec = flat_hit_record(S, L);
 				const DnbMaterial hm = load_material(S, vox_material(rec));
 				const f3 through = vox_albedo(rec) * L.colorMult + L.colorAdd;
 				if(hm.emissive)

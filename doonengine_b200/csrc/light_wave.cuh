@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(WAVE_SERVE_THREADS) dn_wave_serve_kernel(DnbSc
 			L.st.lastVoxID = 255u;
 			L.st.lastVoxRefract = 1.0f;
 			L.st.vox = make_uint4(0, 0, 0, 0);
+			L.chunkOpaque = false; /* (flat_hit_record: the hit's record is settled here, not by the persistent kernel's deferred fetch) */
 			L.st.hitMapIndex = L.st.hitLocalIndex = L.st.hitRecord = 0;
 			if(L.hit)
 			{
