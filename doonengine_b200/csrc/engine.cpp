@@ -144,13 +144,12 @@ void device_destroy(VolumeImpl* v)
 		if(v->frameDone[k]) cudaEventDestroy(v->frameDone[k]);
 		v->frameDone[k] = nullptr;
 	}
-	for(int slot = 0; slot < 2; slot++)
+	for(int i = 0; i < 4; i++)
 	{
-		if(v->tuner.begin[slot]) cudaEventDestroy(v->tuner.begin[slot]);
-		if(v->tuner.end[slot]) cudaEventDestroy(v->tuner.end[slot]);
-		v->tuner.begin[slot] = v->tuner.end[slot] = nullptr;
-		v->tuner.slotKernel[slot] = -1;
+		if(v->tuner.ev[i]) cudaEventDestroy(v->tuner.ev[i]);
+		v->tuner.ev[i] = nullptr;
 	}
+	v->tuner.probeCount = 0;
 	for(int k = 0; k < 2; k++)
 	{
 		if(v->pinnedBlobs[k]) cudaFreeHost(v->pinnedBlobs[k]);
@@ -1385,122 +1384,116 @@ extern "C" bool dnb_light_spread_usable(uint32_t numDiffuseSamples, uint32_t spe
 extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint32_t* requests, const DnbWork* work, uint32_t gridCtas, const DnbStagingTargets* targets, cudaStream_t stream);
 
 /* kernel indices used below: 0 warp per request (light.cu), 1 persistent state machine (light_flat.cuh), 2 wavefront pair
- * (light_wave.cuh), 3 one warp per voxel with its rays spread over the lanes (light_spread.cuh).
+ * (light_wave.cuh), 3 spread: a warp per voxel with specular rays (light_spread.cuh).
  *
  * Auto mode.  The kernels are the same function of the map (tests/test_parity_gpu.py), so choosing between them is purely a question
  * of speed, and that depends on the scene: short rays that end together favour one warp per request, rays of very different length
  * the persistent state machine, and dispatches too small to fill the machine with one thread per voxel the spread kernel (a
- * candidate only up to SPREAD_MAX_REQUESTS requests: it spends a warp per voxel).  Every dispatch is bracketed by two events (no
- * synchronisation: they are read one or two dispatches later, once they have completed anyway); the first dispatches rotate through
- * the candidates until each has two timings (the very first one, the jitter-free first sample, is not representative and is not
- * used), then the fastest one runs, with 5 % hysteresis, and the others are re-timed in turn every 64th dispatch (every 1024th if they were more than twice as slow) in case the camera
- * or the map has changed.  The wavefront pair is not a candidate: measured on B200 after round 2's dropped-item fix it is slower
- * than the persistent kernel on every configuration (profiles/r2_light.md); it stays selectable explicitly. */
+ * candidate only up to SPREAD_MAX_REQUESTS requests).  Timing them on DIFFERENT dispatches does not compare them: every voxel of a
+ * dispatch uses the same random directions (voxelLighting.comp:75,162-168), so one frame of the dense map costs five times another,
+ * and while the visible set still grows the host does not even know a dispatch's size.  So the candidates are timed on the SAME
+ * dispatch: a probe dispatch is split between them, CTA k of this process's share going to candidate k mod n -- statistically the same
+ * work -- and the parts run back to back on the stream with an event in between (no synchronisation: read a dispatch or two later).
+ * Every request is still lit exactly once, so a probe costs only what the slower candidates lose on their part.  Probes: the second
+ * and fourth dispatch of a volume, then every 64th, and whenever the dispatch has grown or shrunk by half since the last one; a
+ * candidate that was more than twice as slow sits out fifteen of sixteen probes.  The faster kernel of the latest probe runs, with
+ * 5 % hysteresis.  The wavefront pair is not a candidate: after round 2's dropped-item fix it is slower than the persistent kernel on
+ * every configuration (profiles/r2_light.md); it stays selectable explicitly. */
 static const size_t SPREAD_MAX_REQUESTS = 8192;
-static int pick_light_kernel(VolumeImpl* v, uint32_t numCtas, bool ctasExact, uint32_t firstCta, uint32_t ctaStride, bool spreadEligible, cudaStream_t s, int* slotOut)
+
+/* reads a finished probe: per-CTA times of its kernels, from the count the device has published for that dispatch */
+static void harvest_probe(VolumeImpl* v)
 {
 	VolumeImpl::LightTuner& t = v->tuner;
-	*slotOut = -1;
+	if(t.probeCount == 0 || cudaEventQuery(t.ev[t.probeCount]) != cudaSuccess)
+	{
+		cudaGetLastError(); /* cudaErrorNotReady is not an error */
+		return;
+	}
+	/* the CTAs the dispatch really had: the host sized it from a count that lags a frame behind; the device has published the real
+	 * one in the meantime (a ring of four words), unless four more syncs have gone by */
+	uint32_t ctas = t.probeCtas;
+	if(!t.probeExact)
+	{
+		if(v->syncSerial - t.probeSerial >= 4u)
+			ctas = 0;
+		else
+		{
+			const uint32_t exact = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars + (t.probeSerial & 3u));
+			const uint32_t total = (exact + 3u) / 4u;
+			ctas = total > t.probeFirstCta ? (total - t.probeFirstCta + t.probeStride - 1u) / t.probeStride : 0u;
+		}
+	}
+	const int n = t.probeCount;
+	t.probeCount = 0;
+	if(ctas < (uint32_t)n)
+		return;
+	double ns[3];
+	for(int i = 0; i < n; i++)
+	{
+		float ms = 0.0f;
+		if(cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) != cudaSuccess)
+			return;
+		ns[i] = 1e6 * (double)ms / (double)((ctas - (uint32_t)i + (uint32_t)n - 1u) / (uint32_t)n);
+	}
+	for(int i = 0; i < n; i++)
+	{
+		t.nsPerCta[t.probeKernels[i]] = ns[i];
+		t.samples[t.probeKernels[i]]++;
+	}
+	/* the incumbent took part in the probe (it always does): switch if another one was at least 5 % faster */
+	int best = -1;
+	double cur = 0.0;
+	for(int i = 0; i < n; i++)
+	{
+		if(t.probeKernels[i] == t.current)
+			cur = ns[i];
+		if(best < 0 || ns[i] < ns[best])
+			best = i;
+	}
+	if(best >= 0 && t.probeKernels[best] != t.current && (cur == 0.0 || ns[best] < 0.95 * cur))
+		t.current = t.probeKernels[best];
+}
+
+/* the kernels of this dispatch: one (returns 1), or the candidates of a probe (returns 2 or 3, the incumbent first) */
+static int pick_light_kernels(VolumeImpl* v, uint32_t numCtas, bool spreadEligible, int kernels[3])
+{
+	VolumeImpl::LightTuner& t = v->tuner;
 	const int mode = light_kernel_choice();
 	if(mode != 2)
-		return mode == 3 ? 2 : mode == 4 ? (spreadEligible ? 3 : 0) : mode;
-
-	/* harvest finished timings */
-	for(int slot = 0; slot < 2; slot++)
 	{
-		if(t.slotKernel[slot] < 0 || cudaEventQuery(t.end[slot]) != cudaSuccess)
-			continue;
-		float ms = 0.0f;
-		/* the CTAs the dispatch really had: the host sized it from a count that lags a frame behind (and while the visible set is
-		 * still growing, by a lot: a kernel timed then looked a hundred times slower per CTA than it is); the device has published
-		 * the real count in the meantime, unless four more syncs have gone by */
-		uint32_t ctas = t.slotCtas[slot];
-		if(!t.slotExact[slot])
-		{
-			if(v->syncSerial - t.slotSerial[slot] >= 4u)
-				ctas = 0;
-			else
-			{
-				const uint32_t exact = *reinterpret_cast<volatile uint32_t*>(v->pinnedScalars + (t.slotSerial[slot] & 3u));
-				const uint32_t total = (exact + 3u) / 4u;
-				ctas = total > t.slotFirstCta[slot] ? (total - t.slotFirstCta[slot] + t.slotStride[slot] - 1u) / t.slotStride[slot] : 0u;
-			}
-		}
-		if(cudaEventElapsedTime(&ms, t.begin[slot], t.end[slot]) == cudaSuccess && ctas > 0)
-		{
-			const int k = t.slotKernel[slot];
-			const double ns = 1e6 * (double)ms / (double)ctas;
-			/* running minimum that may rise by at most 3 % per sample: interference (another process on the box, a clock dip)
-			 * only ever makes a dispatch slower, so one slow sample must not dethrone the faster kernel */
-			t.nsPerCta[k] = t.samples[k] == 0 ? ns : std::min(ns, 1.03 * t.nsPerCta[k]);
-			t.samples[k]++;
-		}
-		t.slotKernel[slot] = -1;
+		kernels[0] = mode == 3 ? 2 : mode == 4 ? (spreadEligible ? 3 : 0) : mode;
+		return 1;
 	}
-	cudaGetLastError(); /* cudaErrorNotReady from the queries above is not an error */
-
-	int cand[3] = {0, 1, 3};
-	const int numCand = spreadEligible ? 3 : 2;
-	int k = -1;
+	harvest_probe(v);
 	const uint64_t n = t.dispatches++;
-	for(int c = 0; c < numCand && k < 0; c++)
-	{
-		/* round robin over the candidates that still lack two timings (the first dispatch of a volume is never timed) */
-		const int o = cand[(int)((n + (uint64_t)c) % (uint64_t)numCand)];
-		if(t.samples[o] < 2)
-			k = o;
-	}
-	if(k < 0)
-	{
-		/* hysteresis: the kernel that ran last keeps running unless another one is at least 5 % faster */
-		int last = cand[0];
-		for(int c = 0; c < numCand; c++)
-			if(cand[c] == t.lastKernel)
-				last = cand[c];
-		int best = cand[0];
-		for(int c = 1; c < numCand; c++)
-			if(t.nsPerCta[cand[c]] < t.nsPerCta[best])
-				best = cand[c];
-		k = (best != last && t.nsPerCta[best] < 0.95 * t.nsPerCta[last]) ? best : last;
-		if((n & 63u) == 63u)
-		{
-			/* keep the other candidates' estimates fresh, in turn */
-			int at = 0;
-			for(int c = 0; c < numCand; c++)
-				if(cand[c] == k)
-					at = c;
-			/* a candidate that was more than twice as slow is looked at 16 times less often: on the demo map one re-timed
-			 * warp-per-request dispatch costs as much as eight dispatches of the kernel that runs */
-			const uint64_t tick = n >> 6;
-			const bool rare = (tick & 15u) == 15u;
-			const int other = cand[(at + 1 + (int)((rare ? tick >> 4 : tick) % (uint64_t)(numCand - 1))) % numCand];
-			if(rare || t.nsPerCta[other] < 2.0 * t.nsPerCta[k])
-				k = other;
-			else
-				t.lastKernel = k;
-		}
-		else
-			t.lastKernel = k;
-	}
+	if(t.current == 3 && !spreadEligible)
+		t.current = 0;
+	kernels[0] = t.current;
 
-	/* time this dispatch if a slot is free (never the first dispatch of a volume) */
-	if(n > 0 && numCtas > 0)
-		for(int slot = 0; slot < 2; slot++)
-			if(t.slotKernel[slot] < 0)
-			{
-				if(!t.begin[slot] && (cudaEventCreate(&t.begin[slot]) != cudaSuccess || cudaEventCreate(&t.end[slot]) != cudaSuccess))
-					break;
-				t.slotKernel[slot] = k;
-				t.slotCtas[slot] = numCtas;
-				t.slotExact[slot] = ctasExact;
-				t.slotSerial[slot] = v->syncSerial;
-				t.slotFirstCta[slot] = firstCta;
-				t.slotStride[slot] = ctaStride ? ctaStride : 1u;
-				cudaEventRecord(t.begin[slot], s);
-				*slotOut = slot;
-				break;
-			}
-	return k;
+	const bool due = n == 1 || n == 3 || n - t.lastProbeAt >= 64u ||
+	                 (t.lastProbeCtas > 0 && n - t.lastProbeAt >= 4u && (numCtas > t.lastProbeCtas + t.lastProbeCtas / 2u || numCtas < t.lastProbeCtas / 2u));
+	if(!due || t.probeCount != 0 || n == 0 || numCtas < 6u)
+		return 1;
+	const bool everyone = (t.probes & 15u) == 15u || t.probes < 2u;
+	int count = 1;
+	const int cand[3] = {0, 1, 3};
+	for(int c = 0; c < 3; c++)
+	{
+		const int k = cand[c];
+		if(k == t.current || (k == 3 && !spreadEligible))
+			continue;
+		/* a candidate that was more than twice as slow in its last probe sits most probes out: on the demo map one part of a probe run
+		 * by the warp-per-request kernel costs as much as eight whole dispatches of the kernel that runs */
+		const bool hopeless = t.samples[k] > 0 && t.nsPerCta[t.current] > 0.0 && t.nsPerCta[k] > 2.0 * t.nsPerCta[t.current];
+		if(hopeless && !everyone)
+			continue;
+		kernels[count++] = k;
+	}
+	t.lastProbeAt = n;
+	t.lastProbeCtas = numCtas;
+	t.probes++;
+	return count;
 }
 
 /* pool size of the wavefront kernels: every voxel of the dispatch in flight at once when that fits, else the cap set with
@@ -1648,35 +1641,80 @@ static bool light_compute(VolumeImpl* v, int numDiffuseSamples, int maxDiffuseSa
 	ScopedTimer timer(&v->stats.lastLightMs, s);
 	bool ok = sync_materials(v, s);
 	ok = ok && cuda_ok(dnb_upload_light_params(&lp, s), "lighting parameters");
-	int timingSlot = -1;
 	const bool spreadEligible = expect <= SPREAD_MAX_REQUESTS && dnb_light_spread_usable(lp.numDiffuseSamples, lp.specularBounceLimit);
-	const int kernel = scene.counters ? 0 : pick_light_kernel(v, numCtas, needExact, firstCta, ctaStride, spreadEligible, s, &timingSlot); /* the instrumented build exists for the warp kernel only */
-	/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself, and so does the persistent kernel
-	 * (4-byte stores as its lanes finish, but overlapped with its ray tracing: measured faster at 8 replicas than a push afterwards,
-	 * 302 vs 349 ns per 4 requests on config 3); the wavefront kernels stage locally and their rows are pushed to the peers
-	 * afterwards (light.cu dn_push_staging_kernel: 323 -> 261 ns at 4 replicas) */
-	DnbStagingTargets allPeers = targets;
-	const bool pushAfter = v->peerAttached && kernel == 2 && targets.count > 1;
-	if(pushAfter)
+	int kernels[3] = {0, -1, -1};
+	const int parts = scene.counters ? 1 : pick_light_kernels(v, numCtas, spreadEligible, kernels); /* the instrumented build exists for the warp kernel only */
+	VolumeImpl::LightTuner& tuner = v->tuner;
+	bool probing = parts > 1;
+	if(probing)
 	{
-		targets.count = 1;
-		targets.dst[0] = allPeers.dst[v->peers.rank];
+		for(int i = 0; i <= parts && probing; i++)
+			if(!tuner.ev[i] && cudaEventCreate(&tuner.ev[i]) != cudaSuccess)
+				probing = false;
+		if(!probing)
+			cudaGetLastError();
 	}
-	if(kernel == 2)
+	const int launches = probing ? parts : 1;
+	if(probing)
 	{
-		const uint32_t P = wave_pool_slots(numCtas);
-		ok = ok && (P == 0 || device_reserve(v->waveCtx, (size_t)P * (dnb_wave_slot_bytes() / sizeof(uint4)), false, false, "wavefront lighting contexts"));
-		ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, &work, &targets, v->waveCtx.ptr, P, v->scalars.ptr + 16, &v->tuner.lastWavePasses, s), "wavefront lighting kernels");
+		tuner.probeSerial = v->syncSerial;
+		tuner.probeExact = needExact;
+		tuner.probeCtas = numCtas;
+		tuner.probeFirstCta = work.firstCta;
+		tuner.probeStride = work.ctaStride ? work.ctaStride : 1u;
+		for(int i = 0; i < parts; i++)
+			tuner.probeKernels[i] = kernels[i];
+		cudaEventRecord(tuner.ev[0], s);
 	}
-	else if(kernel == 3)
-		ok = ok && cuda_ok(dnb_launch_light_spread(&scene, v->requests.ptr, &work, std::max<uint32_t>(numCtas, 1u), &targets, s), "lighting kernel (spread)");
-	else
-		ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, &work, std::max<uint32_t>(numCtas, 1u), &targets, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
-	if(pushAfter)
-		ok = ok && cuda_ok(dnb_launch_push_staging(&allPeers, v->peers.rank, &work, std::max<uint32_t>(numCtas, 1u), s), "staging push");
-	if(timingSlot >= 0)
-		cudaEventRecord(v->tuner.end[timingSlot], s);
-	v->tuner.launches[kernel]++;
+	for(int part = 0; part < launches; part++)
+	{
+		const int kernel = kernels[part];
+		/* a probe's part: every `launches`-th CTA of this process's share, starting with the part's number */
+		DnbWork w = work;
+		uint32_t partCtas = numCtas;
+		if(launches > 1)
+		{
+			const uint32_t stride = work.ctaStride ? work.ctaStride : 1u;
+			w.firstCta = work.firstCta + (uint32_t)part * stride;
+			w.ctaStride = stride * (uint32_t)launches;
+			partCtas = numCtas > (uint32_t)part ? (numCtas - (uint32_t)part + (uint32_t)launches - 1u) / (uint32_t)launches : 0u;
+			if(work.numCtas)
+				w.numCtas = partCtas;
+			if(partCtas == 0)
+			{
+				cudaEventRecord(tuner.ev[part + 1], s);
+				continue;
+			}
+		}
+		/* multi-GPU: the warp-per-request kernel stores its coalesced rows into every replica itself, and so do the persistent and
+		 * spread kernels (4-byte stores as their lanes finish, but overlapped with the ray tracing: measured faster at 8 replicas than
+		 * a push afterwards, 302 vs 349 ns per 4 requests on config 3); the wavefront kernels stage locally and their rows are pushed
+		 * to the peers afterwards (light.cu dn_push_staging_kernel: 323 -> 261 ns at 4 replicas) */
+		DnbStagingTargets to = targets;
+		const bool pushAfter = v->peerAttached && kernel == 2 && targets.count > 1;
+		if(pushAfter)
+		{
+			to.count = 1;
+			to.dst[0] = targets.dst[v->peers.rank];
+		}
+		if(kernel == 2)
+		{
+			const uint32_t P = wave_pool_slots(partCtas);
+			ok = ok && (P == 0 || device_reserve(v->waveCtx, (size_t)P * (dnb_wave_slot_bytes() / sizeof(uint4)), false, false, "wavefront lighting contexts"));
+			ok = ok && cuda_ok(dnb_launch_light_wave(&scene, v->requests.ptr, &w, &to, v->waveCtx.ptr, P, v->scalars.ptr + 16, &tuner.lastWavePasses, s), "wavefront lighting kernels");
+		}
+		else if(kernel == 3)
+			ok = ok && cuda_ok(dnb_launch_light_spread(&scene, v->requests.ptr, &w, std::max<uint32_t>(partCtas, 1u), &to, s), "lighting kernel (spread)");
+		else
+			ok = ok && cuda_ok(dnb_launch_light(&scene, v->requests.ptr, &w, std::max<uint32_t>(partCtas, 1u), &to, kernel == 1 ? v->scalars.ptr + 8 : nullptr, s), "lighting kernel");
+		if(pushAfter)
+			ok = ok && cuda_ok(dnb_launch_push_staging(&targets, v->peers.rank, &w, std::max<uint32_t>(partCtas, 1u), s), "staging push");
+		if(probing)
+			cudaEventRecord(tuner.ev[part + 1], s);
+		tuner.launches[kernel]++;
+	}
+	if(probing)
+		tuner.probeCount = parts;
 	return ok;
 }
 

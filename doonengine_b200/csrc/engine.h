@@ -124,17 +124,21 @@ struct VolumeImpl
 	 * THIS map and camera is found by timing them on live dispatches ---- */
 	struct LightTuner
 	{
-		cudaEvent_t begin[2] = {nullptr, nullptr}, end[2] = {nullptr, nullptr}; /* two timing slots in rotation */
-		int      slotKernel[2] = {-1, -1};   /* kernel timed in each slot, -1 = slot free */
-		uint32_t slotCtas[2] = {0, 0};        /* CTAs of the timed dispatch as the host estimated them ... */
-		bool     slotExact[2] = {false, false}; /* ... which is exact (host-driven sharding), or replaced at harvest by the count the device published: */
-		uint64_t slotSerial[2] = {0, 0};      /* the reading sync whose list the dispatch worked on (pinnedScalars ring) */
-		uint32_t slotFirstCta[2] = {0, 0}, slotStride[2] = {1, 1};
-		double   nsPerCta[4] = {0.0, 0.0, 0.0, 0.0}; /* running estimate per kernel: 0 warp per request, 1 persistent, 2 wavefront, 3 spread */
+		/* a PROBE dispatch is split between the candidate kernels (interleaved CTAs: same frame, same random directions,
+		 * statistically the same work), run back to back on the stream with an event between them; read a frame or two later */
+		cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+		int      probeKernels[3] = {-1, -1, -1};
+		int      probeCount = 0;               /* kernels of the probe in flight, 0 = none */
+		uint64_t probeSerial = 0;              /* the reading sync whose list the probe worked on (pinnedScalars ring) */
+		bool     probeExact = false;           /* probeCtas is exact (host-driven sharding) */
+		uint32_t probeCtas = 0, probeFirstCta = 0, probeStride = 1;
+		double   nsPerCta[4] = {0.0, 0.0, 0.0, 0.0}; /* latest probe result per kernel: 0 warp per request, 1 persistent, 2 wavefront, 3 spread */
 		uint32_t samples[4] = {0, 0, 0, 0};
-		uint64_t dispatches = 0;
+		uint64_t dispatches = 0, probes = 0;
+		uint64_t lastProbeAt = 0;
+		uint32_t lastProbeCtas = 0;
 		uint64_t launches[4] = {0, 0, 0, 0};
-		int      lastKernel = 1;
+		int      current = 0;                  /* the kernel that runs between probes */
 		uint32_t lastWavePasses = 0;
 	} tuner;
 

@@ -18,12 +18,13 @@ pytestmark = pytest.mark.gpu
 W, H, FRAMES = 320, 192, 4
 
 
-@pytest.fixture(autouse=True, params=["flat", "warp", "wave", "spread"])
+@pytest.fixture(autouse=True, params=["flat", "warp", "wave", "spread", "auto"])
 def light_kernel(request, dn):
     """every test of this module runs against all four lighting kernels: the persistent state machine (light_flat.cuh), the
     one-warp-per-request kernel (light.cu), the wavefront pair (light_wave.cuh) and the one-warp-per-voxel kernel for small dispatches
-    (light_spread.cuh); their results must be the same bits."""
-    dn.lib().DN_b200_set_light_kernel({"warp": 0, "flat": 1, "wave": 3, "spread": 4}[request.param])
+    (light_spread.cuh); their results must be the same bits.  "auto" is the library's default: its probe dispatches (the second and
+    fourth of every volume) are SPLIT between the candidate kernels, CTA by CTA, which must not show in the result either."""
+    dn.lib().DN_b200_set_light_kernel({"warp": 0, "flat": 1, "auto": 2, "wave": 3, "spread": 4}[request.param])
     yield request.param
     dn.lib().DN_b200_set_light_kernel(2)  # back to auto
 
