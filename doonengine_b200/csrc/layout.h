@@ -132,6 +132,8 @@ typedef struct DnbFlatTuning
 {
 	int budget, endLanes, patience;
 	int endMax; /* 1: finished rays are also served as soon as they are the most populated state of the warp */
+	int keep;   /* a stepping phase goes on while at least keep/8 of the lanes it started with are still in it */
+	int run;    /* > 0: a stepping phase is exactly this many steps instead (no vote inside the loop) */
 } DnbFlatTuning;
 
 /* the staging arrays one lighting launch stores into: its own, or every replica's */

@@ -520,7 +520,7 @@ __global__ void dn_merge_visible_peers_kernel(DnbPeerTable T, uint32_t* __restri
 #include "light_wave.cuh"
 #include "light_spread.cuh"
 
-static DnbFlatTuning g_flatTuning = {0, 0, 0, 0};
+static DnbFlatTuning g_flatTuning = {0, 0, 0, 0, 0, 0};
 
 /* scheduling knobs of the persistent kernel (experiments; results do not depend on them) */
 extern "C" void DN_b200_set_flat_tuning(int budget, int endLanes, int patience)
@@ -567,7 +567,7 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 			auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
 			tuning.budget = knob("DN_B200_FLAT_BUDGET", 24);
 			tuning.endLanes = knob("DN_B200_FLAT_END", 20);
-			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 32);
+			tuning.patience = knob("DN_B200_FLAT_PATIENCE", 48);
 		}
 		static int endMax = -1;
 		if(endMax < 0)
@@ -576,6 +576,20 @@ extern "C" cudaError_t dnb_launch_light(const DnbScene* scene, const uint32_t* r
 			endMax = e ? atoi(e) != 0 : 0;
 		}
 		tuning.endMax = endMax;
+		static int keep = -1;
+		if(keep < 0)
+		{
+			const char* e = getenv("DN_B200_FLAT_KEEP");
+			keep = e && atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : 2;
+		}
+		tuning.keep = keep;
+		static int run = -1;
+		if(run < 0)
+		{
+			const char* e = getenv("DN_B200_FLAT_RUN");
+			run = e && atoi(e) > 0 ? atoi(e) : 0;
+		}
+		tuning.run = run;
 		{ DNB_LAUNCHED(1); dn_light_flat_kernel<<<grid, FLAT_WARPS * 32, 0, stream>>>(*scene, requests, *work, flatCounter, *targets, tuning); }
 	}
 	else

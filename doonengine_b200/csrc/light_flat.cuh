@@ -35,6 +35,10 @@
 #ifndef FLAT_DEFER_RECORD
 #define FLAT_DEFER_RECORD 1
 #endif
+/* two steps per census of a stepping phase (A/B builds) */
+#ifndef FLAT_UNROLL2
+#define FLAT_UNROLL2 0
+#endif
 
 enum : uint32_t { ST_FETCH = 0, ST_TILE = 1, ST_VOX = 2, ST_END = 3, ST_DONE = 4, ST_ENTER = 5 };
 enum : uint32_t { RAY_SPEC = 0, RAY_DIFFUSE = 1, RAY_SHADOW = 2 };
@@ -409,6 +413,24 @@ DNB_FN uint4 flat_hit_record(const DnbScene& S, FlatLane& L)
 DNB_FN bool flat_ray_ended(const DnbScene& S, const DnbStagingTargets& T, FlatLane& L, uint32_t& state)
 {
 	const f3 sunDir = ld3(c_light.sunDir);
+	/* the record and the material of the voxel that was hit, for the ray kinds that look at them (LI:107-109 specular, LI:176-178
+	 * diffuse: not when the hit is the neighbouring voxel): fetched HERE, for all lanes of the phase together -- two dependent loads
+	 * once, not once per kind of ray */
+	uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+	DnbMaterial hm = {};
+	bool shade = false;
+	if(L.hit && L.kind != RAY_SHADOW)
+	{
+		const f3 from = L.kind == RAY_SPEC ? L.pa : L.origin;
+		const f3 dist = abs3(floor3(L.pos * 8.0f) - floor3(from * 8.0f));
+		const float d2 = dot3(dist, dist);
+		shade = L.kind == RAY_SPEC ? !(d2 <= 1.0f) : !(d2 < 1.0f);
+		if(shade)
+		{
+			rec = flat_hit_record(S, L);
+			hm = load_material(S, vox_material(rec));
+		}
+	}
 	if(L.kind == RAY_SPEC)
 	{
 		if(L.hit)
@@ -421,11 +443,8 @@ DNB_FN bool flat_ray_ended(const DnbScene& S, const DnbStagingTargets& T, FlatLa
 				if(!(__ldcg(S.propagate + (hitIndex >> 5)) & bit))
 					atomicOr(S.propagate + (hitIndex >> 5), bit);
 			}
-			const f3 dist = abs3(floor3(L.pos * 8.0f) - floor3(L.pa * 8.0f));
-			if(!(dot3(dist, dist) <= 1.0f))
+			if(shade)
 			{
-				const uint4 rec = flat_hit_record(S, L);
-				const DnbMaterial hm = load_material(S, vox_material(rec));
 				const f3 hitAlbedo = vox_albedo(rec);
 				const f3 hitDiffuse = vox_diffuse(rec) * (1.0f - hm.specular);
 				if(hm.emissive)
@@ -468,11 +487,8 @@ DNB_FN bool flat_ray_ended(const DnbScene& S, const DnbStagingTargets& T, FlatLa
 	{
 		if(L.hit)
 		{
-			const f3 dist = abs3(floor3(L.origin * 8.0f) - floor3(L.pos * 8.0f));
-			if(!(dot3(dist, dist) < 1.0f))
+			if(shade)
 			{
-				const uint4 rec = flat_hit_record(S, L);
-				const DnbMaterial hm = load_material(S, vox_material(rec));
 				const f3 through = vox_albedo(rec) * L.colorMult + L.colorAdd;
 				if(hm.emissive)
 					L.diff = L.diff + L.pa * through;
@@ -652,27 +668,37 @@ __global__ void __launch_bounds__(FLAT_WARPS * 32, FLAT_MIN_BLOCKS) dn_light_fla
 		}
 		else if(nT >= nV)
 		{
-			const int keep = (3 * nT + 3) >> 2;
+			const int keep = (K.keep * nT + 7) >> 3;
 #pragma unroll 1
 			for(int it = 0; it < K.budget; it++)
 			{
 				if(state == ST_TILE)
 					flat_tile_step(S, L, state);
 				waited++;
-				if(__popc(__ballot_sync(0xFFFFFFFFu, state == ST_TILE)) < keep)
+#if FLAT_UNROLL2
+				if(state == ST_TILE)
+					flat_tile_step(S, L, state);
+				waited++;
+#endif
+				if(K.run ? it + 1 >= K.run : __popc(__ballot_sync(0xFFFFFFFFu, state == ST_TILE)) < keep)
 					break;
 			}
 		}
 		else
 		{
-			const int keep = (3 * nV + 3) >> 2;
+			const int keep = (K.keep * nV + 7) >> 3;
 #pragma unroll 1
 			for(int it = 0; it < K.budget; it++)
 			{
 				if(state == ST_VOX)
 					flat_vox_step(S, L, state);
 				waited++;
-				if(__popc(__ballot_sync(0xFFFFFFFFu, state == ST_VOX)) < keep)
+#if FLAT_UNROLL2
+				if(state == ST_VOX)
+					flat_vox_step(S, L, state);
+				waited++;
+#endif
+				if(K.run ? it + 1 >= K.run : __popc(__ballot_sync(0xFFFFFFFFu, state == ST_VOX)) < keep)
 					break;
 			}
 		}

@@ -18,9 +18,10 @@
  * words are bit-identical to the other kernels' (tests/test_parity_gpu.py runs every lighting test against this kernel too).
  *
  * What DOES carry from ray to ray inside a shader invocation is the "inside a transparent block" state (lastVoxID / lastVoxRefract,
- * SH:324-325) and the guard flag; a ray that ends inside glass or trips changes how the next one starts.  Every lane starts clean, as
- * the first ray does; if any ray of the voxel does not also END clean, the warp discards its work and lane 0 lights the voxel the serial
- * way (light_voxel), which is exact by construction.  Rare: it takes a ray that hits an opaque voxel without leaving the glass first.
+ * SH:324-325) and the guard flag; a ray that ends inside glass changes how the next one starts.  Every lane first starts clean, as the
+ * first ray does; then a lane whose predecessor (in the shader's order) ended inside glass traces its ray again from that state, until
+ * no lane's start differs from its predecessor's end.  On the demo map, where glass panes touch floors and walls, the earlier scheme --
+ * discard everything and let lane 0 light the voxel serially -- made those voxels the tail of the whole dispatch.
  */
 #define SPREAD_WARPS 4
 
@@ -86,32 +87,56 @@ __global__ void __launch_bounds__(SPREAD_WARPS * 32, 5) dn_light_spread_kernel(D
 		const f3 viewDir = rayPos - ld3(c_light.camPos);
 		const bool diffuse = material.specular < 1.0f;
 
-		/* ---- this lane's ray ---- */
+		/* ---- this lane's ray ----
+		 * Every ray is first traced as if it started outside any transparent block (lastVoxID = 255), which is how the first ray starts.
+		 * Then each lane looks at the state its PREDECESSOR in the shader's order ended in (specular 0..14, then diffuse path and shadow
+		 * ray of sample 0, of sample 1, ...); a lane whose predecessor ended inside glass traces its ray again from that state, which
+		 * may change how IT ends, and so on until nothing changes -- at most one round per ray, normally none or one. */
+		const bool hasRay = lane < 15u || (diffuse && lane < 15u + 2u * n);
+		const uint32_t predLane = lane == 0u ? 0u : lane < 15u ? lane - 1u : lane == 15u ? 14u : lane < 15u + n ? lane + n - 1u : lane - n;
+		uint32_t startID = 255u;
+		float startRefract = 1.0f;
+		bool redo = hasRay, broken = false;
 		AccList acc;
 		acc.n = 0;
 		acc.numTiles = 0;
-		if(lane < 15u)
+#pragma unroll 1
+		for(uint32_t round = 0; round < 32u; round++)
 		{
+			if(redo)
 			{
-				const f3 reflected = reflect3(normalize3(viewDir), normal);
-				const f3 specDir = normalize3(reflected * (float)material.shininess + ld3(c_spherePoints[lane])) + DNB_EPSILON;
-				specular_ray<false>(S, cx, rayPos, specDir, albedo, material.reflectType, acc);
+				ray_state_reset(cx.st);
+				cx.st.lastVoxID = startID;
+				cx.st.lastVoxRefract = startRefract;
+				acc.n = 0;
+				acc.numTiles = 0;
+				if(lane < 15u)
+				{
+					const f3 reflected = reflect3(normalize3(viewDir), normal);
+					const f3 specDir = normalize3(reflected * (float)material.shininess + ld3(c_spherePoints[lane])) + DNB_EPSILON;
+					specular_ray<false>(S, cx, rayPos, specDir, albedo, material.reflectType, acc);
+				}
+				else if(lane < 15u + n)
+					diffuse_ray<false>(S, cx, normal + DNB_EPSILON, rayPos, rec, lane - 15u, acc);
+				else
+					shadow_ray<false>(S, cx, rayPos, lane - 15u - n, acc);
+				broken = broken || cx.st.tripped || acc.n > (uint32_t)DNB_MAX_ADDENDS || acc.numTiles > (uint32_t)DNB_MAX_ADDENDS;
 			}
-		}
-		else if(lane < 15u + n)
-		{
-			if(diffuse)
-				diffuse_ray<false>(S, cx, normal + DNB_EPSILON, rayPos, rec, lane - 15u, acc);
-		}
-		else if(lane < 15u + 2u * n)
-		{
-			if(diffuse)
-				shadow_ray<false>(S, cx, rayPos, lane - 15u - n, acc);
+			const uint32_t predID = __shfl_sync(0xFFFFFFFFu, cx.st.lastVoxID, predLane);
+			const float predRefract = __shfl_sync(0xFFFFFFFFu, cx.st.lastVoxRefract, predLane);
+			redo = hasRay && lane != 0u && (predID != startID || __float_as_uint(predRefract) != __float_as_uint(startRefract));
+			if(redo)
+			{
+				startID = predID;
+				startRefract = predRefract;
+			}
+			if(!__any_sync(0xFFFFFFFFu, redo) || __any_sync(0xFFFFFFFFu, broken))
+				break;
 		}
 
-		/* did every ray end the way the next one must start? */
-		const bool dirty = cx.st.lastVoxID != 255u || cx.st.tripped || acc.n > (uint32_t)DNB_MAX_ADDENDS || acc.numTiles > (uint32_t)DNB_MAX_ADDENDS;
-		if(__any_sync(0xFFFFFFFFu, dirty))
+		/* a guard that tripped stays tripped for the rest of the invocation, and a ray with more addends than a lane keeps cannot be
+		 * replayed: lane 0 lights such a voxel the serial way (never seen on the test maps) */
+		if(__any_sync(0xFFFFFFFFu, broken || redo))
 		{
 			if(lane == 0)
 			{

@@ -39,7 +39,7 @@ def env_knob(name, dflt):
 
 
 # the persistent kernel's knobs: from the environment when set there (DN_B200_FLAT_ENDMAX is read by the library itself)
-flat_knobs = (env_knob("DN_B200_FLAT_BUDGET", 24), env_knob("DN_B200_FLAT_END", 20), env_knob("DN_B200_FLAT_PATIENCE", 32))
+flat_knobs = (env_knob("DN_B200_FLAT_BUDGET", 24), env_knob("DN_B200_FLAT_END", 20), env_knob("DN_B200_FLAT_PATIENCE", 48))
 variants = [(n, flat_knobs if n == "flat" else None) for n in names]
 out = []
 k = 0
