@@ -106,7 +106,7 @@ DNB_FN void shadow_ray(const DnbScene& S, LightCtx& cx, f3 rayPos, uint32_t samp
 
 	f3 tmpNormal = splat3(0.0f), colorAdd;
 	float colorMult;
-	if(!trace_ray<false, COUNT>(S, cx.st, cx.lc, dir, rcp3(dir), rayPos, true, tmpNormal, colorAdd, colorMult))
+	if(!trace_ray<false, COUNT, true>(S, cx.st, cx.lc, dir, rcp3(dir), rayPos, true, tmpNormal, colorAdd, colorMult))
 		color.add(ld3(S.sunStrength) * colorMult + colorAdd);
 }
 

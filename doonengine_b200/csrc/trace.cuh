@@ -174,8 +174,14 @@ DNB_FN void cull_undo(uint32_t& offp, i3& pos, uint32_t& bias)
 /* step_map + step_chunk.  REFRACT: enableRefraction (true in draw, false in lighting, DR:65 / LI:209); only then is
  * hitNormal read or written.  invRayDir is by value: a refraction inside a chunk updates the caller's rayDir but only
  * this function's invRayDir, exactly as the inout/in qualifiers at SH:328/421 do.
- * COUNT: instrumented build -- exact per-tile bounds checks and counters, no empty-block fast path. */
-template <bool REFRACT, bool COUNT>
+ * COUNT: instrumented build -- exact per-tile bounds checks and counters, no empty-block fast path.
+ * OCCLUSION: the caller only asks WHETHER the ray hits an opaque voxel (the shadow ray, LI:77-79): in a chunk whose materials are all
+ * opaque the voxel's bit answers that, and neither the record nor the hit position is produced (st.vox, st.hit*, rayPos are left
+ * alone; the shadow ray reads none of them, and every ray that follows sets what it reads). */
+#ifndef DNB_OCCLUSION_RAYS
+#define DNB_OCCLUSION_RAYS 1
+#endif
+template <bool REFRACT, bool COUNT, bool OCCLUSION = false>
 DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayDir, f3 invRayDir, f3& rayPos, bool ignoreFirst, f3& hitNormal, f3& colorAdd, float& colorMult)
 {
 	colorAdd = splat3(0.0f);
@@ -305,6 +311,8 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 
 				if(((word >> (local & 31u)) & 1u) && !ignoreFirst)
 				{
+					if(OCCLUSION && DNB_OCCLUSION_RAYS && !COUNT && chunkOpaque)
+						return true;
 					/* SH:150-169 with per-word prefix counts instead of quarter counts */
 					const uint32_t rel = (uint32_t)DNB_LDG(slot->prefix + wordIdx) + DNB_POPC(word & ((1u << (local & 31u)) - 1u));
 					const uint4 rec = DNB_LDG(S.records + (DNB_LDG(&slot->voxelBase) + rel));
