@@ -238,40 +238,52 @@ def run_reference(args, scene, tiles, res, desc):
         return
     chunks, camera = make_chunks(scene, tiles) if scene != "demo" else ([], {})
     kind = "reference" if O.have_ref() else "port"
-    # the reference's host code dispatching the reference's OWN shaders (their GLSL text compiled as C++ where it lies, oracle/glsl/),
-    # when that library was built; else the reference's host code dispatching the restatement of the shaders; else the restated host
-    shaders = "reference GLSL compiled as C++ (oracle/_ref/libglsl_ref.so)" if kind == "reference" and O.have_glsl() else "CPU restatement (oracle/shader_cpu.c)"
     import functools
-    cls = (functools.partial(O.RefEngine, glsl=True) if O.have_glsl() else O.RefEngine) if kind == "reference" else O.OracleEngine
-    # the reference sizes its voxel pool as 512*minChunks/2 (voxel.c:190): twice the chunk count keeps everything resident
-    e = build_engine(cls, scene, tiles, chunks, camera, min_chunks=2 * len(chunks) + 32)
-    e.sync(1, 1)
-    # SAME config as the GPU arm: the draw runs at the config's full resolution, so both arms light the same visible set
-    # (a 1920x1080 draw + sync + lighting dispatch of config 2 takes ~0.2 s on 16 cores: W + K steps stay within seconds)
-    lit, t_light, t_frame, reqs = 0, 0.0, 0.0, 0
-    for k in range(args.warmup + args.steps):
-        e.reset_counters()
-        t0 = time.perf_counter()
-        e.draw(w, h)
-        e.sync(2, 1)
-        t1 = time.perf_counter()
-        e.update_lighting(1, 1000, frame_time(k))
-        t2 = time.perf_counter()
-        if k >= args.warmup:
-            lit += lit_by_requests(e) if kind == "reference" else e.counters()["light"]["voxelsLit"]
-            t_light += t2 - t1
-            t_frame += t2 - t0
-            reqs += len(e.requests())
-    value = lit / t_light if t_light > 0 else 0.0
+    # the device behind the reference's host code: the reference's OWN shaders (their GLSL text compiled as C++ where it lies,
+    # oracle/glsl/) and the hand restatement of them that is pinned to that text bit for bit (oracle/shader_cpu.c, the leaner code).
+    # Both are timed; the line's value is the FASTER of the two, so the baseline is the best this host can do with the reference's path.
+    variants = []
+    if kind == "reference":
+        if O.have_glsl():
+            variants.append(("reference GLSL compiled as C++ (oracle/_ref/libglsl_ref.so)", functools.partial(O.RefEngine, glsl=True)))
+        variants.append(("CPU restatement pinned to it (oracle/shader_cpu.c)", O.RefEngine))
+    else:
+        variants.append(("CPU restatement (oracle/shader_cpu.c)", O.OracleEngine))
+    results = []
+    for shaders, cls in variants:
+        # the reference sizes its voxel pool as 512*minChunks/2 (voxel.c:190): twice the chunk count keeps everything resident
+        e = build_engine(cls, scene, tiles, chunks, camera, min_chunks=2 * len(chunks) + 32)
+        e.sync(1, 1)
+        # SAME config as the GPU arm: the draw runs at the config's full resolution, so both arms light the same visible set
+        lit, t_light, t_frame, reqs = 0, 0.0, 0.0, 0
+        for k in range(args.warmup + args.steps):
+            e.reset_counters()
+            t0 = time.perf_counter()
+            e.draw(w, h)
+            e.sync(2, 1)
+            t1 = time.perf_counter()
+            e.update_lighting(1, 1000, frame_time(k))
+            t2 = time.perf_counter()
+            if k >= args.warmup:
+                lit += lit_by_requests(e) if kind == "reference" else e.counters()["light"]["voxelsLit"]
+                t_light += t2 - t1
+                t_frame += t2 - t0
+                reqs += len(e.requests())
+        e.close()
+        results.append({"shaders": shaders, "value": lit / t_light if t_light > 0 else 0.0, "e2e": lit / t_frame if t_frame > 0 else 0.0,
+                        "ms_per_step": 1000.0 * t_frame / max(args.steps, 1), "lit": lit, "reqs": reqs})
+    best = max(results, key=lambda r: r["value"])
+    value, lit, reqs, t_frame = best["value"], best["lit"], best["reqs"], best["ms_per_step"] * max(args.steps, 1) / 1000.0
     K = max(args.steps, 1)
     sample = "each step = %dx%d draw + sync + 1 lighting dispatch over the chunks that draw made visible (%d requests, %d voxels lit per step), %d OpenMP threads; host: %s; shaders: %s" % (
-        w, h, reqs // K, lit // K, cores, "reference voxel.c (oracle/_ref/libdoon_ref.so)" if kind == "reference" else "restated (oracle/host_cpu.c)", shaders)
+        w, h, reqs // K, lit // K, cores, "reference voxel.c (oracle/_ref/libdoon_ref.so)" if kind == "reference" else "restated (oracle/host_cpu.c)", best["shaders"])
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_frame / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": desc, "frame": "draw -> sync(READ_WRITE,1) -> update_lighting(1,1000,t)", "resolution": [w, h],
                                          "requests_per_step": reqs / K, "voxels_lit_per_step": lit / K},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "variants": [{"shaders": r["shaders"], "value": r["value"], "e2e": r["e2e"], "ms_per_step": r["ms_per_step"]} for r in results]},
         "e2e": {"value": lit / t_frame if t_frame > 0 else 0.0, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "glsl_baseline": gl_probe(),
     }), flush=True)

@@ -1395,7 +1395,8 @@ extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint
  * dispatch: a probe dispatch is split between them, CTA k of this process's share going to candidate k mod n -- statistically the same
  * work -- and the parts run back to back on the stream with an event in between (no synchronisation: read a dispatch or two later).
  * Every request is still lit exactly once, so a probe costs only what the slower candidates lose on their part.  Probes: the second
- * and fourth dispatch of a volume, then every 64th, and whenever the dispatch has grown or shrunk by half since the last one; a
+ * and fourth dispatch of a volume, then every 64th, and whenever the dispatch has grown or shrunk by a quarter since the last one (while
+ * the visible set of a new camera position is still growing, that is every other dispatch); a
  * candidate that was more than twice as slow sits out fifteen of sixteen probes.  The faster kernel of the latest probe runs, with
  * 5 % hysteresis.  The wavefront pair is not a candidate: after round 2's dropped-item fix it is slower than the persistent kernel on
  * every configuration (profiles/r2_light.md); it stays selectable explicitly. */
@@ -1472,7 +1473,7 @@ static int pick_light_kernels(VolumeImpl* v, uint32_t numCtas, bool spreadEligib
 	kernels[0] = t.current;
 
 	const bool due = n == 1 || n == 3 || n - t.lastProbeAt >= 64u ||
-	                 (t.lastProbeCtas > 0 && n - t.lastProbeAt >= 4u && (numCtas > t.lastProbeCtas + t.lastProbeCtas / 2u || numCtas < t.lastProbeCtas / 2u));
+	                 (t.lastProbeCtas > 0 && n - t.lastProbeAt >= 2u && (numCtas > t.lastProbeCtas + t.lastProbeCtas / 4u || numCtas < t.lastProbeCtas - t.lastProbeCtas / 4u));
 	if(!due || t.probeCount != 0 || n == 0 || numCtas < 6u)
 		return 1;
 	const bool everyone = (t.probes & 15u) == 15u || t.probes < 2u;

@@ -140,10 +140,13 @@ DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 	Dda& m = L.m;
 	if((uint32_t)((m.pos.x ^ L.blk.x) | (m.pos.y ^ L.blk.y) | (m.pos.z ^ L.blk.z)) > 3u)
 	{
-		if(!in_map_bounds(S, m.pos) ||
-		   (m.pos.x > S.occMax[0] && m.step.x >= 0) || (m.pos.x < S.occMin[0] && m.step.x <= 0) ||
+		if(!in_map_bounds(S, m.pos)
+#if DNB_EARLYOUT_EVERY_BLOCK
+		   || (m.pos.x > S.occMax[0] && m.step.x >= 0) || (m.pos.x < S.occMin[0] && m.step.x <= 0) ||
 		   (m.pos.y > S.occMax[1] && m.step.y >= 0) || (m.pos.y < S.occMin[1] && m.step.y <= 0) ||
-		   (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0))
+		   (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0)
+#endif
+		  )
 		{
 			state = ST_END; /* miss */
 			return;
@@ -161,6 +164,15 @@ DNB_FN void flat_tile_step(const DnbScene& S, FlatLane& L, uint32_t& state)
 
 	if(L.occWord == 0ull)
 	{
+		/* exact early-out (trace.cuh): past the bounding box of everything resident and moving away; tested in empty blocks only */
+		if(!DNB_EARLYOUT_EVERY_BLOCK &&
+		   ((m.pos.x > S.occMax[0] && m.step.x >= 0) || (m.pos.x < S.occMin[0] && m.step.x <= 0) ||
+		    (m.pos.y > S.occMax[1] && m.step.y >= 0) || (m.pos.y < S.occMin[1] && m.step.y <= 0) ||
+		    (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0)))
+		{
+			state = ST_END; /* miss */
+			return;
+		}
 		/* empty block: the bare recurrence until the ray leaves it */
 		do
 		{

@@ -178,6 +178,10 @@ DNB_FN void cull_undo(uint32_t& offp, i3& pos, uint32_t& bias)
  * OCCLUSION: the caller only asks WHETHER the ray hits an opaque voxel (the shadow ray, LI:77-79): in a chunk whose materials are all
  * opaque the voxel's bit answers that, and neither the record nor the hit position is produced (st.vox, st.hit*, rayPos are left
  * alone; the shadow ray reads none of them, and every ray that follows sets what it reads). */
+/* 1 = test the early-out at every block change, as before (A/B builds) */
+#ifndef DNB_EARLYOUT_EVERY_BLOCK
+#define DNB_EARLYOUT_EVERY_BLOCK 0
+#endif
 #ifndef DNB_OCCLUSION_RAYS
 #define DNB_OCCLUSION_RAYS 1
 #endif
@@ -214,12 +218,12 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 				/* entered another 4x4x4 block: the only place the map bounds are tested */
 				if(!in_map_bounds(S, m.pos))
 					break;
-				/* exact early-out: past the bounding box of everything resident and moving away from it, the ray can
-				 * only miss, and nothing of its DDA state is used after a miss */
+#if DNB_EARLYOUT_EVERY_BLOCK
 				if(!COUNT && ((m.pos.x > S.occMax[0] && m.step.x >= 0) || (m.pos.x < S.occMin[0] && m.step.x <= 0) ||
 				              (m.pos.y > S.occMax[1] && m.step.y >= 0) || (m.pos.y < S.occMin[1] && m.step.y <= 0) ||
 				              (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0)))
 					break;
+#endif
 				blk.x = m.pos.x & ~3; blk.y = m.pos.y & ~3; blk.z = m.pos.z & ~3;
 				occWord = DNB_LDG(S.occ64 + ((uint32_t)(m.pos.x >> 2) + S.blocks[0] * ((uint32_t)(m.pos.y >> 2) + S.blocks[1] * (uint32_t)(m.pos.z >> 2))));
 			}
@@ -235,6 +239,15 @@ DNB_FN bool trace_ray(const DnbScene& S, RayState& st, DnbCounters& lc, f3& rayD
 
 			if(!COUNT && occWord == 0ull)
 			{
+				/* exact early-out: past the bounding box of everything resident and moving away from it, the ray can only miss, and
+				 * nothing of its DDA state is used after a miss.  Tested in EMPTY blocks only -- a block with anything in it lies
+				 * inside the box or straddles its border, and a ray that is past the border there reaches an empty block next --
+				 * so rays inside the populated region never pay for the twelve comparisons */
+				if(!DNB_EARLYOUT_EVERY_BLOCK &&
+				   ((m.pos.x > S.occMax[0] && m.step.x >= 0) || (m.pos.x < S.occMin[0] && m.step.x <= 0) ||
+				    (m.pos.y > S.occMax[1] && m.step.y >= 0) || (m.pos.y < S.occMin[1] && m.step.y <= 0) ||
+				    (m.pos.z > S.occMax[2] && m.step.z >= 0) || (m.pos.z < S.occMin[2] && m.step.z <= 0)))
+					break;
 				/* the whole block is empty (or padding outside the map): run the bare DDA recurrence until the ray leaves it */
 				do
 				{

@@ -8,7 +8,8 @@
  *
  * The shaders are racy where oracle.h says so; the buffer proxies below give one dispatch the determinism rules N1-N3 WITHOUT touching
  * the shader text:
- *   voxels[i]        reads come from a snapshot taken at dispatch start (N1); field stores go to the live buffer
+ *   voxels[i]        field stores are held back in a side array and applied after the dispatch, so every read sees the pre-dispatch
+ *                    value (N1) -- without copying the whole pool per dispatch, which would cost more than the dispatch itself
  *   chunks[i]        numIndirectSamples reads see the pre-dispatch value, `++` is applied once after the dispatch (N2)
  *   map[i].flags     reads see the pre-dispatch value; `&= ~4` / `|= 4` are recorded and applied after the dispatch, clears first (N3);
  *                    `= 3` (a stream request, voxelShared.comp:464) is applied directly -- it never happens in resident mode
@@ -18,6 +19,7 @@
 #include "glsl_compat.h"
 #include "../oracle.h"
 
+#include <omp.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -29,7 +31,7 @@ struct Device
 {
 	const OrbBuffers*  buf;
 	const OrbUniforms* u;
-	const OrbVoxel*    voxelSnap;
+	OrbVoxel*          pending;      /* held-back voxel stores (lighting only), indexed like voxels[]; a record is valid once written */
 	uint8_t*           setVisible;   /* per tile */
 	uint8_t*           clearVisible; /* per tile */
 	uint32_t*          sampleIncrements; /* per tile */
@@ -43,10 +45,11 @@ struct ShaderBase;
 /* ---- voxels[] ---- */
 struct VoxelField
 {
-	uint32_t* live;
-	const uint32_t* snap;
-	void operator=(uint v) { *live = v; }
-	operator uint() const { return *snap; }
+	ShaderBase* inv;
+	uint index;
+	int field; /* word of the record */
+	void operator=(uint v);
+	operator uint() const;
 };
 struct VoxelRef
 {
@@ -187,6 +190,7 @@ struct ShaderBase
 	/* instrumentation (not visible to the shader text) */
 	uint lastVoxelRead;
 	int  visibleSetAt;
+	uint writtenVoxel; /* the one voxel this invocation has stored to, 0xFFFFFFFF = none yet */
 
 	explicit ShaderBase(Device* d) : dev(d)
 	{
@@ -214,6 +218,7 @@ struct ShaderBase
 		gl_WorkGroupSize = uvec3(1, 1, 1);
 		lastVoxelRead = 0xFFFFFFFFu;
 		visibleSetAt = -1;
+		writtenVoxel = 0xFFFFFFFFu;
 	}
 
 	ivec2 imageSize(const image2D&) const { return ivec2(dev->w, dev->h); }
@@ -237,11 +242,26 @@ inline void FlagsRef::operator|=(uint m)
 
 inline VoxelRef VoxelArr::operator[](uint i) const
 {
-	Device* d = inv->dev;
-	OrbVoxel* live = d->buf->voxels + i;
-	const OrbVoxel* snap = d->voxelSnap + i;
-	VoxelRef r = {inv, i, {&live->normal, &snap->normal}, {&live->albedo, &snap->albedo}, {&live->specLight, &snap->specLight}, {&live->diffuseLight, &snap->diffuseLight}};
+	VoxelRef r = {inv, i, {inv, i, 0}, {inv, i, 1}, {inv, i, 2}, {inv, i, 3}};
 	return r;
+}
+
+inline VoxelField::operator uint() const
+{
+	return reinterpret_cast<const uint32_t*>(inv->dev->buf->voxels + index)[field];
+}
+
+inline void VoxelField::operator=(uint v)
+{
+	Device* d = inv->dev;
+	if(!d->pending || (inv->writtenVoxel != 0xFFFFFFFFu && inv->writtenVoxel != index))
+		abort(); /* the draw shader stores no voxel; a lighting invocation stores only its own */
+	if(inv->writtenVoxel == 0xFFFFFFFFu)
+	{
+		d->pending[index] = d->buf->voxels[index];
+		inv->writtenVoxel = index;
+	}
+	reinterpret_cast<uint32_t*>(d->pending + index)[field] = v;
 }
 
 template <class T> VoxelRef::operator T() const
@@ -283,7 +303,7 @@ extern "C" void glsl_draw(const OrbBuffers* buf, const OrbUniforms* u, int w, in
 	std::vector<uint8_t> setV(tiles ? tiles : 1, 0);
 	Device dev;
 	memset(&dev, 0, sizeof(dev));
-	dev.buf = buf; dev.u = u; dev.voxelSnap = buf->voxels; dev.setVisible = setV.data(); dev.clearVisible = nullptr; dev.sampleIncrements = nullptr;
+	dev.buf = buf; dev.u = u; dev.pending = nullptr; dev.setVisible = setV.data(); dev.clearVisible = nullptr; dev.sampleIncrements = nullptr;
 	dev.image = image; dev.w = w; dev.h = h;
 	const int gx = w / 16, gy = h / 16;
 	#pragma omp parallel for schedule(dynamic, 1) collapse(2)
@@ -321,11 +341,15 @@ extern "C" void glsl_light(const OrbBuffers* buf, const OrbUniforms* u, const ui
 	const size_t tiles = (size_t)u->mapSize[0] * u->mapSize[1] * u->mapSize[2];
 	std::vector<uint8_t> setV(tiles ? tiles : 1, 0), clearV(tiles ? tiles : 1, 0);
 	std::vector<uint32_t> inc(tiles ? tiles : 1, 0);
-	std::vector<OrbVoxel> snap(buf->voxels, buf->voxels + numVoxelRecords);
+	/* untouched pages of this array are never mapped: only the records the dispatch stores to cost anything */
+	OrbVoxel* pending = static_cast<OrbVoxel*>(malloc((numVoxelRecords ? numVoxelRecords : 1) * sizeof(OrbVoxel)));
+	if(!pending)
+		abort();
 	Device dev;
 	memset(&dev, 0, sizeof(dev));
-	dev.buf = buf; dev.u = u; dev.voxelSnap = snap.data(); dev.setVisible = setV.data(); dev.clearVisible = clearV.data(); dev.sampleIncrements = inc.data();
+	dev.buf = buf; dev.u = u; dev.pending = pending; dev.setVisible = setV.data(); dev.clearVisible = clearV.data(); dev.sampleIncrements = inc.data();
 	dev.requests = requests;
+	std::vector<std::vector<uint32_t>> written((size_t)omp_get_max_threads());
 	#pragma omp parallel for schedule(dynamic, 4)
 	for(long long g = 0; g < (long long)numRequests; g++)
 		for(uint lane = 0; lane < 32; lane++)
@@ -336,7 +360,13 @@ extern "C" void glsl_light(const OrbBuffers* buf, const OrbUniforms* u, const ui
 			s.gl_WorkGroupSize = uvec3(32, 1, 1);
 			s.gl_GlobalInvocationID = uvec3((uint)g * 32u + lane, 0, 0);
 			s.shader_main();
+			if(s.writtenVoxel != 0xFFFFFFFFu)
+				written[(size_t)omp_get_thread_num()].push_back(s.writtenVoxel);
 		}
+	for(const std::vector<uint32_t>& list : written)
+		for(uint32_t i : list)
+			buf->voxels[i] = pending[i];
+	free(pending);
 	apply_flags(buf, tiles, clearV.data(), setV.data(), inc.data());
 }
 

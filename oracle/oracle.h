@@ -23,7 +23,7 @@
  *                (oracle/glsl/translate.py does the syntax, glsl_compat.h the types and built-ins, glsl_harness.cpp the dispatch);
  *                tests/test_glsl_pin.py: shader_cpu.c produces the same pixels, first hits, lit words, visible flags and sample
  *                counts, bit for bit, over the demo map, a glass / edit / lightingSplit scene and the three synthetic maps.
- *   fixtures     tests/golden/*.npz are written by the two together (reference host dispatching reference shaders, nothing
+ *   fixtures     tests/golden/ (the .npz files) are written by the two together (reference host dispatching reference shaders, nothing
  *                restated: tests/golden/make_golden.py) and checked wherever the suite runs, incl. the GPU box.
  * The reference ships no tests, golden vectors or KATs of its own.  What remains DEFINED rather than pinned
  * are the points where GLSL itself leaves the result to the implementation or the shaders race -- rules N1-N11 below; both
