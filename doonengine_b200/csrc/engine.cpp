@@ -1395,10 +1395,11 @@ extern "C" cudaError_t dnb_launch_light_spread(const DnbScene* scene, const uint
  * dispatch: a probe dispatch is split between them, CTA k of this process's share going to candidate k mod n -- statistically the same
  * work -- and the parts run back to back on the stream with an event in between (no synchronisation: read a dispatch or two later).
  * Every request is still lit exactly once, so a probe costs only what the slower candidates lose on their part.  Probes: the second
- * and fourth dispatch of a volume, then every 64th, and whenever the dispatch has grown or shrunk by a quarter since the last one (while
+ * and fourth dispatch of a volume, then every 8th to 64th (the closer the best two, the sooner), and whenever the dispatch has grown or shrunk by a quarter since the last one (while
  * the visible set of a new camera position is still growing, that is every other dispatch); a
- * candidate that was more than twice as slow sits out fifteen of sixteen probes.  The faster kernel of the latest probe runs, with
- * 5 % hysteresis.  The wavefront pair is not a candidate: after round 2's dropped-item fix it is slower than the persistent kernel on
+ * candidate that was more than twice as slow sits out fifteen of sixteen probes.  The estimates are smoothed over probes (one frame's
+ * random directions can favour either kernel) and start over when the dispatch changes size; the fastest estimate runs, with 5 %
+ * hysteresis.  The wavefront pair is not a candidate: after round 2's dropped-item fix it is slower than the persistent kernel on
  * every configuration (profiles/r2_light.md); it stays selectable explicitly. */
 static const size_t SPREAD_MAX_REQUESTS = 8192;
 
@@ -1437,23 +1438,43 @@ static void harvest_probe(VolumeImpl* v)
 			return;
 		ns[i] = 1e6 * (double)ms / (double)((ctas - (uint32_t)i + (uint32_t)n - 1u) / (uint32_t)n);
 	}
+	/* one frame's random directions can favour either kernel (on the dense map the ratio swings between 0.7 and 1.9 from frame to
+	 * frame), so the estimates are smoothed over probes -- and start over when the dispatch has changed size by a quarter, because
+	 * per-CTA times of a half-empty machine say nothing about a full one */
+	if(t.regimeCtas == 0 || ctas > t.regimeCtas + t.regimeCtas / 4u || ctas < t.regimeCtas - t.regimeCtas / 4u)
+	{
+		t.regimeCtas = ctas;
+		for(int k = 0; k < 4; k++)
+			t.samples[k] = 0;
+	}
 	for(int i = 0; i < n; i++)
 	{
-		t.nsPerCta[t.probeKernels[i]] = ns[i];
-		t.samples[t.probeKernels[i]]++;
+		const int k = t.probeKernels[i];
+		t.nsPerCta[k] = t.samples[k] == 0 ? ns[i] : 0.5 * t.nsPerCta[k] + 0.5 * ns[i];
+		t.samples[k]++;
 	}
-	/* the incumbent took part in the probe (it always does): switch if another one was at least 5 % faster */
+	/* the fastest estimate runs, with 5 % hysteresis in favour of the incumbent; the closer the runner-up, the sooner the next probe */
 	int best = -1;
-	double cur = 0.0;
-	for(int i = 0; i < n; i++)
+	double second = 0.0;
+	for(int k = 0; k < 4; k++)
 	{
-		if(t.probeKernels[i] == t.current)
-			cur = ns[i];
-		if(best < 0 || ns[i] < ns[best])
-			best = i;
+		if(t.samples[k] == 0)
+			continue;
+		if(best < 0 || t.nsPerCta[k] < t.nsPerCta[best])
+		{
+			if(best >= 0)
+				second = second == 0.0 ? t.nsPerCta[best] : std::min(second, t.nsPerCta[best]);
+			best = k;
+		}
+		else
+			second = second == 0.0 ? t.nsPerCta[k] : std::min(second, t.nsPerCta[k]);
 	}
-	if(best >= 0 && t.probeKernels[best] != t.current && (cur == 0.0 || ns[best] < 0.95 * cur))
-		t.current = t.probeKernels[best];
+	if(best < 0)
+		return;
+	if(best != t.current && (t.samples[t.current] == 0 || t.nsPerCta[best] < 0.95 * t.nsPerCta[t.current]))
+		t.current = best;
+	const double ratio = second > 0.0 ? second / t.nsPerCta[best] : 1.0;
+	t.probeInterval = ratio > 2.0 ? 64u : ratio > 1.3 ? 16u : 8u;
 }
 
 /* the kernels of this dispatch: one (returns 1), or the candidates of a probe (returns 2 or 3, the incumbent first) */
@@ -1472,7 +1493,7 @@ static int pick_light_kernels(VolumeImpl* v, uint32_t numCtas, bool spreadEligib
 		t.current = 0;
 	kernels[0] = t.current;
 
-	const bool due = n == 1 || n == 3 || n - t.lastProbeAt >= 64u ||
+	const bool due = n == 1 || n == 3 || n - t.lastProbeAt >= t.probeInterval ||
 	                 (t.lastProbeCtas > 0 && n - t.lastProbeAt >= 2u && (numCtas > t.lastProbeCtas + t.lastProbeCtas / 4u || numCtas < t.lastProbeCtas - t.lastProbeCtas / 4u));
 	if(!due || t.probeCount != 0 || n == 0 || numCtas < 6u)
 		return 1;

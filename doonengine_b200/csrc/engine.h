@@ -132,7 +132,9 @@ struct VolumeImpl
 		uint64_t probeSerial = 0;              /* the reading sync whose list the probe worked on (pinnedScalars ring) */
 		bool     probeExact = false;           /* probeCtas is exact (host-driven sharding) */
 		uint32_t probeCtas = 0, probeFirstCta = 0, probeStride = 1;
-		double   nsPerCta[4] = {0.0, 0.0, 0.0, 0.0}; /* latest probe result per kernel: 0 warp per request, 1 persistent, 2 wavefront, 3 spread */
+		double   nsPerCta[4] = {0.0, 0.0, 0.0, 0.0}; /* per kernel, smoothed over the probes it took part in: 0 warp per request, 1 persistent, 2 wavefront, 3 spread */
+		uint32_t probeInterval = 8;            /* dispatches between probes: short while the best two are close, long when one is far ahead */
+		uint32_t regimeCtas = 0;               /* dispatch size the estimates belong to; they start over when it changes by a quarter */
 		uint32_t samples[4] = {0, 0, 0, 0};
 		uint64_t dispatches = 0, probes = 0;
 		uint64_t lastProbeAt = 0;
