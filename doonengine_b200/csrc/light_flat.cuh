@@ -5,27 +5,34 @@
  * warp walks the nested loops (rays -> tiles -> voxels) together, so every loop runs until its slowest lane is done:
  * ncu showed 13-15 of 32 lanes active on the terrain map and far fewer on sparse maps, where one ray of a warp crosses
  * a hundred tiles while the others hit a neighbour at once.  Here every lane carries the complete state of its voxel
- * AND of the ray it is tracing, and is always in one of four states:
+ * AND of the ray it is tracing, and is always in one of five states:
  *
  *     TILE   stepping the tile-level DDA                       (phase A of trace_ray)
+ *     ENTER  has found a resident chunk: slot lookup, entry cell, bounding-box offsets (~95 instructions, two dependent loads)
  *     VOX    stepping the voxel-level DDA inside a chunk       (phase B of trace_ray)
- *     END    its ray has ended: shade it, advance the voxel's ray schedule (specular rays, diffuse bounces, shadow
- *            ray), start the next ray, or store the voxel's result ...
+ *     END    its ray has ended: fetch the record it hit (opaque hits leave that to this phase), shade it, advance the voxel's
+ *            ray schedule (specular rays, diffuse bounces, shadow ray), start the next ray, or store the voxel's result ...
  *     FETCH  ... and take the next voxel from a global work counter (persistent warps, dynamic fetch)
  *
- * Each trip round the warp's loop counts the lanes per state and runs ONE phase:
+ * Each trip round the warp's loop takes a census of the lanes' states (four ballots) and runs ONE phase:
  *   serve   (END / FETCH lanes) once `endLanes` lanes wait for it, or nothing else can run, or the waiting lanes have sat
  *           through `patience` stepping iterations: ray set-up and shading is by far the most expensive phase, so it should
  *           run with as many lanes as possible, but a few very long rays must not hold everybody up;
- *   TILE or VOX burst   the stepping phase with more lanes, until fewer than 3/4 of its lanes are still stepping.
+ *   ENTER   when it is the most populated state;
+ *   TILE or VOX burst   the stepping phase with more lanes, until fewer than keep/8 of its lanes are still stepping.
  * A lane that finishes early is not idle until the warp's slowest ray ends; it waits only until enough other lanes want
  * the same phase.  Nothing about a voxel's own sequence of operations changes, so the staged words are bit-identical to
- * dn_light_kernel's (tests/test_parity_gpu.py runs every lighting test against both kernels).
+ * dn_light_kernel's (tests/test_parity_gpu.py runs every lighting test against every kernel).
  *
- * Measured (B200, profiles/r1_light_kernels.md): 2.6x faster than dn_light_kernel on the sparse map and 2.5x on the bundled
- * demo map, where ray lengths inside a warp differ wildly; 1.4x SLOWER on the terrain map, whose rays are a handful of steps
- * long and end together (there the state machine's bookkeeping and the fragmented voxel set-up outweigh the better lane use).
- * The host therefore times both on live dispatches and runs the faster one (engine.cpp pick_light_kernel).
+ * The rule that emerged in round 2 (profiles/r2_light.md sections 8-9): whatever is rare per step and dear per occurrence must be a
+ * batched phase, not code inline in a step where it runs with the 2-4 lanes that happen to need it in the same iteration (chunk
+ * entry, the record -> material fetch of a hit), and phases must be long, because the census costs as much as a step.  Defaults
+ * (light.cu): endLanes 20, patience 48, keep 2/8; sparse 1024^3 dispatch 143 -> 106 ms, 9.7 -> 13.3 active lanes per instruction.
+ *
+ * Measured (B200, profiles/r2_light.md section 6 and r2_bench_*.json): the fastest kernel on the sparse map (111 vs ~210 ms per
+ * dispatch at 1024^3) and on the edit-stream map; slower than dn_light_kernel on the terrain map (0.91 vs 0.42 ms), whose rays are a
+ * handful of steps long and end together, and on late frames of the dense map.  The host times the candidates on live dispatches,
+ * split between them, and runs the fastest (engine.cpp pick_light_kernels).
  *
  * The ray-persistent state of one shader invocation (lastVoxID / lastVoxRefract / voxel, SH:321-325) is per lane and
  * reset per voxel, as one invocation lights one voxel.  Lighting never refracts (LI:209), so the chunk-level DDA shares

@@ -47,18 +47,23 @@ typedef struct DNb200hit { int32_t status; uint32_t mapIndex, localIndex, record
 bool DN_b200_capture_hits(GLuint fb, bool enable);
 bool DN_b200_read_hits(GLuint fb, DNb200hit* dst, size_t count);
 
-/* ---- lighting kernel choice: 0 = one warp per lighting request (the reference's work-group shape, voxel.c:950 / LI:3),
- * 1 = persistent warps running every voxel as a state machine with dynamic work fetch (same results bit for bit),
+/* ---- lighting kernel choice (all of them produce the same bits):
+ * 0 = one warp per lighting request (the reference's work-group shape, voxel.c:950 / LI:3),
+ * 1 = persistent warps running every voxel as a state machine with dynamic work fetch,
  * 3 = wavefront: voxel contexts in device memory, a full-warp shading / ray set-up kernel alternating with a persistent
- *     ray-stepping kernel (same results bit for bit; fastest on large maps with rays of very different length),
- * 2 = auto (default): all three are timed on live dispatches of this volume and the fastest one runs.
- * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat" | "wave" | "auto". ---- */
+ *     ray-stepping kernel (selectable; no longer a candidate of the automatic choice),
+ * 4 = spread, for small dispatches: a voxel with specular rays gets a whole warp, its rays side by side (falls back to 0 when a
+ *     dispatch asks for more than 8 diffuse samples or 4 specular bounces),
+ * 2 = auto (default): now and then a dispatch is SPLIT between the candidates (0, 1 and, up to 8 192 requests, 4), CTA by CTA, each
+ *     part timed; the fastest runs until the next such probe (engine.cpp pick_light_kernels).
+ * Initial value from $DN_B200_LIGHT_KERNEL = "warp" | "flat" | "wave" | "spread" | "auto". ---- */
 void DN_b200_set_light_kernel(int which);
 int  DN_b200_get_light_kernel(void);
 /* context-pool size of the wavefront kernels (rounded to a multiple of 128; 0 = default / $DN_B200_WAVE_SLOTS = 4 Mi slots of 240
  * bytes).  A dispatch with more voxels than slots is streamed through the pool; results do not depend on the size. */
 void DN_b200_set_wave_slots(uint32_t slots);
-/* scheduling knobs of the persistent kernel (see csrc/light_flat.cuh); results do not depend on them.  0 = defaults / environment */
+/* scheduling knobs of the persistent kernel (see csrc/light_flat.cuh); results do not depend on them.  0 = defaults / environment
+ * ($DN_B200_FLAT_BUDGET 24, $DN_B200_FLAT_END 20, $DN_B200_FLAT_PATIENCE 48; also $DN_B200_FLAT_KEEP 2, in eighths) */
 void DN_b200_set_flat_tuning(int budget, int endLanes, int patience);
 
 /* ---- request list ---- */
