@@ -37,6 +37,33 @@ def test_reference_arm_json_line():
     assert "%dx%d draw" % bench.CONFIGS["small"][2] in cb["sample"]
     assert cb["cores"] == os.cpu_count() or cb["cores"] == len(os.sched_getaffinity(0))
     assert d["glsl_baseline"].startswith("unavailable (") or d["glsl_baseline"].startswith("available")
+    # every variant of the reference's device that exists here was timed; the line's value is the faster one
+    variants = cb["variants"]
+    assert variants and max(v["value"] for v in variants) == d["value"]
+    from oracle import oracle as O
+    if O.have_ref() and O.have_glsl():
+        assert len(variants) == 2 and "GLSL compiled as C++" in variants[0]["shaders"]
+
+
+def test_lit_count_from_request_list_equals_the_oracles_counter():
+    """the reference's shaders keep no counters, so the reference arm counts the voxels a dispatch lit from its request list and the
+    chunk buffer's bit masks (bench.lit_by_requests); on the restated shaders, which do count, both must agree"""
+    from oracle import oracle as O
+    O.build()
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/libdoon_ref.so not built (needs /root/reference)")
+    import bench
+    scene, tiles, res, _ = bench.CONFIGS["small"]
+    chunks, camera = bench.make_chunks(scene, tiles)
+    e = bench.build_engine(O.RefEngine, scene, tiles, chunks, camera, min_chunks=2 * len(chunks) + 32)
+    e.sync(1, 1)
+    for k in range(2):
+        e.reset_counters()
+        e.draw(*res)
+        e.sync(2, 2 if k else 1)  # (a lighting split leaves partial request lists)
+        e.update_lighting(1, 1000, bench.frame_time(k))
+        assert bench.lit_by_requests(e) == e.counters()["light"]["voxelsLit"] > 0
+    e.close()
 
 
 def test_reference_arm_other_ranks_do_nothing():
