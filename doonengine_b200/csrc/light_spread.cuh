@@ -24,9 +24,13 @@
  * discard everything and let lane 0 light the voxel serially -- made those voxels the tail of the whole dispatch.
  */
 #define SPREAD_WARPS 4
+/* resident CTAs per SM the register allocation aims for (A/B builds: 5 = 96 registers, 6 = 80, 8 = 64) */
+#ifndef SPREAD_MIN_BLOCKS
+#define SPREAD_MIN_BLOCKS 5
+#endif
 
 template <int DUMMY>
-__global__ void __launch_bounds__(SPREAD_WARPS * 32, 5) dn_light_spread_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W, DnbStagingTargets T)
+__global__ void __launch_bounds__(SPREAD_WARPS * 32, SPREAD_MIN_BLOCKS) dn_light_spread_kernel(DnbScene S, const uint32_t* __restrict__ requests, DnbWork W, DnbStagingTargets T)
 {
 	__shared__ float s_add[SPREAD_WARPS][32][DNB_MAX_ADDENDS][3];
 	__shared__ uint32_t s_num[SPREAD_WARPS][32];
