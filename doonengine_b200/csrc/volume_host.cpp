@@ -48,7 +48,10 @@ static void clear_chunk(DNvolume* vol, size_t index)
 	for(int x = 0; x < DN_CHUNK_SIZE; x++)
 		for(int y = 0; y < DN_CHUNK_SIZE; y++)
 			for(int z = 0; z < DN_CHUNK_SIZE; z++)
+			{
 				c->voxels[x][y][z].normal = UINT32_MAX;
+				c->voxels[x][y][z].albedo = 0; /* (upstream leaves the albedo word of an empty voxel as malloc returned it; nobody reads it, but saved files and test comparisons should not depend on heap garbage) */
+			}
 }
 
 } // namespace dnb

@@ -280,6 +280,45 @@ def test_bulk_chunks_equal_single_chunks(dn):
     b.close()
 
 
+def test_bulk_voxel_edits_equal_single_edits(dn):
+    """DN_b200_set_voxels (an edit list: sets, removals, positions outside the map, edits into tiles without a chunk) leaves the host
+    map exactly as the same sequence of DN_set_compressed_voxel / DN_remove_voxel calls does (voxel.c:1126-1183)."""
+    from doonengine_b200 import scenes
+    tiles = (6, 5, 4)
+    rng = np.random.default_rng(11)
+    a = dn.Engine(map_size=tiles, min_chunks=4, host_only=True)
+    b = dn.Engine(map_size=tiles, min_chunks=4, host_only=True)
+    for p, v in scenes.sparse_balls(tiles):
+        a.set_chunk(p, v)
+        b.set_chunk(p, v)
+    n = 4000
+    pos = rng.integers(-3, [tiles[0] * 8 + 3, tiles[1] * 8 + 3, tiles[2] * 8 + 3], size=(n, 3)).astype(np.int32)
+    pos[::7] = pos[3]  # the same voxel edited again and again: order matters
+    vox = np.empty((n, 2), np.uint32)
+    mat = rng.integers(0, 6, n).astype(np.uint32)
+    mat[rng.random(n) < 0.4] = 255  # removals
+    vox[:, 0] = (mat << 24) | rng.integers(0, 1 << 24, n).astype(np.uint32)
+    vox[:, 1] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & np.uint32(0xFFFFFF00)
+    inside = ((pos >= 0) & (pos < np.array(tiles) * 8)).all(axis=1)
+    assert b.set_voxels(pos, vox) == int(inside.sum())
+    for (x, y, z), (nw, aw), ok in zip(pos.tolist(), vox.tolist(), inside.tolist()):
+        if not ok:
+            continue
+        mp, cp = (x // 8, y // 8, z // 8), (x % 8, y % 8, z % 8)
+        if (nw >> 24) == 255:
+            a.remove_voxel(mp, cp)
+        else:
+            a.set_voxel(mp, cp, nw, aw)
+    ma, mb = a.host_map(), b.host_map()
+    assert np.array_equal(ma["flag"], mb["flag"])
+    ca, cb = a.host_chunks(), b.host_chunks()
+    for t in np.nonzero(ma["flag"])[0]:
+        x, y = ca[ma["chunkIndex"][t]], cb[mb["chunkIndex"][t]]
+        assert x["numVoxels"] == y["numVoxels"] and np.array_equal(x["voxels"], y["voxels"]) and x["updated"] == y["updated"]
+    a.close()
+    b.close()
+
+
 def _check_picks(e, g, name):
     hit = g[name + "_hit"].astype(bool)
     steps = int(g[name + "_steps"])
